@@ -1,0 +1,145 @@
+"""ctypes binding of libn1b200.so (include/n1b200.h).  PyTorch is used for device memory and streams only.
+
+There is deliberately no fallback: if the shared library is missing, or no sm_100 device is present when a
+compute entry point is called, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libn1b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p, c_int, c_size_t, c_float, c_char_p = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_char_p)
+
+
+class N1Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("n1b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class TensorDesc(ctypes.Structure):
+    _fields_ = [("name", c_char_p), ("data", c_void_p), ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * 4)]
+
+
+class S1Dims(ctypes.Structure):
+    _fields_ = [("token_dim", ctypes.c_int32), ("heads", ctypes.c_int32), ("layers", ctypes.c_int32),
+                ("predict_size", ctypes.c_int32), ("memory_size", ctypes.c_int32),
+                ("vlm_token_dim", ctypes.c_int32), ("n_query", ctypes.c_int32)]
+
+
+# every symbol include/n1b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "n1_version": (c_char_p, []),
+    "n1_device_ok": (c_int, [c_int]),
+    "n1_create": (c_int, [ctypes.POINTER(c_void_p), c_int]),
+    "n1_destroy": (None, [c_void_p]),
+    "n1_last_error": (c_char_p, []),
+    "n1_s1_load": (c_int, [c_void_p, ctypes.POINTER(S1Dims), ctypes.POINTER(TensorDesc), c_int, c_void_p]),
+    "n1_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    "n1_rgbd_encode": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "n1_goal_compress": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "n1_navdp_eps": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_void_p]),
+    "n1_navdp_sample": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_int, c_void_p]),
+    "n1_ddpm_tables": (c_int, [c_int, ctypes.POINTER(c_float)]),
+    "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           c_void_p, c_int, c_int, c_int, c_void_p]),
+    "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
+                                c_void_p]),
+    "n1_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+}
+
+OP_RGBD, OP_GOAL, OP_DENOISE = 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SWIGLU = 0, 1, 2, 3
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    "%s not found: build it with `python -m internnav_b200.build` (nvcc, sm_100a). "
+                    "There is no CPU/PyTorch fallback for the n1b200 hot path." % LIB_PATH)
+            L = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise N1Error(code, lib().n1_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "n1b200 takes contiguous CUDA tensors"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError("n1b200 takes fp32 or bf16 tensors, got %s" % t.dtype)
+
+
+# ------------------------------------------------------------------------------------------ kernel-level ops
+def gemm(a, w, bias=None, gamma=None, residual=None, act=ACT_NONE, out_fp32=False, out=None):
+    """out = epi(a @ w.T); a [M,K] bf16 (row stride allowed), w [N,K] bf16."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    check(lib().n1_op_gemm(c_void_p(a.data_ptr()), a.stride(0), c_void_p(w.data_ptr()), w.stride(0),
+                           c_void_p(out.data_ptr()), out.stride(0), M, N, K, ptr(bias), ptr(gamma),
+                           c_void_p(residual.data_ptr()) if residual is not None else None,
+                           residual.stride(0) if residual is not None else 0, act, 1 if out_fp32 else 0, stream_ptr()))
+    return out
+
+
+def layernorm(x, w, b=None, eps=1e-5, rms=False):
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(lib().n1_op_layernorm(c_void_p(x.data_ptr()), x.stride(0), ptr(y), y.stride(0), ptr(w), ptr(b), x.shape[0],
+                                x.shape[1], eps, 1 if rms else 0, stream_ptr()))
+    return y
+
+
+def attention(q, k, v, heads_q, heads_kv, head_dim, batch, seq_q, seq_k, cu_q=None, cu_k=None, max_seq_q=0, kv_div=1,
+              causal=False, scale=None):
+    """q [rows_q, >=heads_q*hd], k/v [rows_k, >=heads_kv*hd] bf16 views with unit inner stride -> o [rows_q, heads_q*hd]."""
+    assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    o = torch.empty(q.shape[0], heads_q * head_dim, device=q.device, dtype=torch.bfloat16)
+    if scale is None:
+        scale = head_dim ** -0.5
+    check(lib().n1_op_attention(c_void_p(q.data_ptr()), c_void_p(k.data_ptr()), c_void_p(v.data_ptr()), ptr(o),
+                                q.stride(0), k.stride(0), v.stride(0), o.stride(0), heads_q, heads_kv, head_dim, batch,
+                                seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div, 1 if causal else 0,
+                                float(scale), stream_ptr()))
+    return o

@@ -1,0 +1,203 @@
+// extern "C" surface of libn1b200.so (include/n1b200.h).  Exceptions stop here and become error codes.
+#include <string.h>
+
+#include <string>
+
+#include "../../include/n1b200.h"
+#include "n1_ops.h"
+#include "s1_model.h"
+#include "weights.h"
+
+using namespace n1;
+
+struct n1_ctx {
+  int device = 0;
+  S1Model s1;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+template <typename F>
+int guard(F&& f) {
+  try {
+    f();
+    return N1_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return N1_ERR_UNKNOWN;
+  } catch (...) {
+    g_err = "unknown error";
+    return N1_ERR_UNKNOWN;
+  }
+}
+
+void require_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw Error(N1_ERR_NO_DEVICE, "no CUDA device visible; n1b200 has no CPU fallback");
+  if (device < 0 || device >= n) throw Error(N1_ERR_NO_DEVICE, "device index out of range");
+  cudaDeviceProp p;
+  N1_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) throw Error(N1_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(p.major) + std::to_string(p.minor) + "; n1b200 kernels are sm_100a only");
+}
+
+void use(n1_handle h) {
+  if (!h) throw Error(N1_ERR_ARG, "null handle");
+  N1_CUDA(cudaSetDevice(h->device));
+}
+
+WeightSource to_source(const n1_tensor_desc* t, int n) {
+  WeightSource ws;
+  for (int i = 0; i < n; ++i) {
+    if (!t[i].name || !t[i].data) throw Error(N1_ERR_WEIGHT, "tensor descriptor with null name/data");
+    SrcTensor s;
+    s.data = t[i].data;
+    s.dtype = t[i].dtype;
+    if (s.dtype != N1_F32 && s.dtype != N1_BF16) throw Error(N1_ERR_WEIGHT, std::string("unsupported dtype for ") + t[i].name);
+    for (int d = 0; d < t[i].ndim && d < 4; ++d) s.shape.push_back(t[i].shape[d]);
+    ws.add(t[i].name, s);
+  }
+  return ws;
+}
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline const bf16* B16(const void* p) { return static_cast<const bf16*>(p); }
+inline bf16* B16(void* p) { return static_cast<bf16*>(p); }
+
+}  // namespace
+
+extern "C" {
+
+const char* n1_version(void) { return "n1b200 0.1 (sm_100a)"; }
+
+const char* n1_last_error(void) { return g_err.c_str(); }
+
+int n1_device_ok(int device) {
+  try {
+    require_device(device);
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
+}
+
+int n1_create(n1_handle* out, int device) {
+  return guard([&] {
+    if (!out) throw Error(N1_ERR_ARG, "null out pointer");
+    require_device(device);
+    N1_CUDA(cudaSetDevice(device));
+    n1_ctx* c = new n1_ctx();
+    c->device = device;
+    *out = c;
+  });
+}
+
+void n1_destroy(n1_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+int n1_s1_load(n1_handle h, const n1_s1_dims* d, const n1_tensor_desc* tensors, int n, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!d || !tensors || n <= 0) throw Error(N1_ERR_ARG, "n1_s1_load: null dims/tensors");
+    S1Dims dims;
+    dims.D = d->token_dim, dims.heads = d->heads, dims.layers = d->layers, dims.T = d->predict_size;
+    dims.frames = d->memory_size, dims.vlm_dim = d->vlm_token_dim, dims.n_query = d->n_query;
+    h->s1.load(to_source(tensors, n), dims, S(stream));
+  });
+}
+
+size_t n1_workspace_bytes(n1_handle h, int op, int B, int Ns, int T) {
+  size_t r = 0;
+  guard([&] {
+    if (!h) throw Error(N1_ERR_ARG, "null handle");
+    switch (op) {
+      case N1_OP_RGBD: r = h->s1.ws_rgbd(B); break;
+      case N1_OP_GOAL: r = h->s1.ws_goal(B); break;
+      case N1_OP_DENOISE: r = h->s1.ws_denoise(B, Ns, T); break;
+      default: throw Error(N1_ERR_ARG, "unknown op");
+    }
+  });
+  return r;
+}
+
+int n1_rgbd_encode(n1_handle h, void* ws, size_t ws_bytes, const float* rgb, const float* depth, void* out, int B,
+                   void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.rgbd_encode(ws, ws_bytes, rgb, depth, B16(out), B, S(stream));
+  });
+}
+
+int n1_goal_compress(n1_handle h, void* ws, size_t ws_bytes, const void* latents, void* goal, int B, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.goal_compress(ws, ws_bytes, B16(latents), B16(goal), B, S(stream));
+  });
+}
+
+int n1_navdp_eps(n1_handle h, void* ws, size_t ws_bytes, const float* x_t, const int32_t* timesteps, int t_scalar,
+                 const void* goal, const void* rgbd, float* eps, int B, int Ns, int T, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.navdp_eps(ws, ws_bytes, x_t, timesteps, t_scalar, B16(goal), B16(rgbd), eps, B, Ns, T, S(stream));
+  });
+}
+
+int n1_navdp_sample(n1_handle h, void* ws, size_t ws_bytes, const void* goal, const void* rgbd, const float* x_init,
+                    const float* step_noise, float* traj_out, int B, int Ns, int T, int K, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.navdp_sample(ws, ws_bytes, B16(goal), B16(rgbd), x_init, step_noise, traj_out, B, Ns, T, K, S(stream));
+  });
+}
+
+int n1_ddpm_tables(int K, float* out_host) {
+  return guard([&] {
+    if (K <= 0 || !out_host) throw Error(N1_ERR_ARG, "n1_ddpm_tables: bad arguments");
+    std::vector<DdpmCoef> c;
+    S1Model::ddpm_tables(K, c);
+    for (int i = 0; i < K; ++i) {
+      out_host[i * 5 + 0] = c[i].sqrt_one_minus_acp, out_host[i * 5 + 1] = c[i].inv_sqrt_acp;
+      out_host[i * 5 + 2] = c[i].c0, out_host[i * 5 + 3] = c[i].c1, out_host[i * 5 + 4] = c[i].sigma;
+    }
+  });
+}
+
+int n1_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+               const float* bias, const float* gamma, const void* residual, int ldr, int act, int out_fp32,
+               void* stream) {
+  return guard([&] {
+    GemmEpilogue e;
+    e.bias = bias, e.gamma = gamma, e.residual = B16(residual), e.ldr = ldr, e.act = act, e.out_fp32 = out_fp32;
+    gemm_bf16(B16(A), lda, B16(W), ldw, out, ldo, M, N, K, e, S(stream));
+  });
+}
+
+int n1_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* w, const float* b, int rows, int D, float eps,
+                    int rms, void* stream) {
+  return guard([&] { layernorm(B16(x), ldx, B16(y), ldy, w, b, rows, D, eps, rms, S(stream)); });
+}
+
+int n1_op_attention(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo, int heads_q,
+                    int heads_kv, int head_dim, int batch, int seq_q, int seq_k, const int32_t* cu_q,
+                    const int32_t* cu_k, int max_seq_q, int kv_div, int causal, float scale, void* stream) {
+  return guard([&] {
+    AttnParams p = {};
+    p.q = B16(q), p.k = B16(k), p.v = B16(v), p.o = B16(o);
+    p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.ldo = ldo;
+    p.heads_q = heads_q, p.heads_kv = heads_kv, p.hd = head_dim, p.batch = batch;
+    p.seq_q = seq_q, p.seq_k = seq_k, p.cu_q = cu_q, p.cu_k = cu_k, p.max_seq_q = max_seq_q;
+    p.kv_div = kv_div < 1 ? 1 : kv_div, p.causal = causal, p.scale = scale;
+    attention(p, S(stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] @ W[N,K]^T).
+//
+//   warp 0        TMA producer   (cp.async.bulk.tensor 2-D, 128-byte swizzle, STAGES-deep mbarrier ring)
+//   warp 1        TMEM allocator + tcgen05.mma issuer (one elected lane; M=128, N=BN, K=16 per instruction)
+//   warps 2..9    epilogue: tcgen05.ld (TMEM -> registers), bias / activation / layer-scale / residual,
+//                 bf16 (or fp32) vector stores.  Two accumulator stages in TMEM so the epilogue of tile i
+//                 overlaps the main loop of tile i+1.
+//
+// This one kernel carries every Linear / Conv-as-GEMM on the InternVLA-N1 hot path:
+// the reference reaches cuBLAS through nn.Linear at navdp.py L57-66/L94-100, navdp_backbone.py L147-149,
+// dinov2_layers/{attention.py L46-48, mlp.py L30-32, patch_embed.py L65} and the Qwen2.5-VL blocks.
+#include <mutex>
+
+#include "n1_ops.h"
+#include "n1_ptx.cuh"
+
+namespace n1 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int tiles_m, tiles_n;
+  void* out;
+  int ldo;
+  const float* bias;
+  const float* gamma;
+  const bf16* residual;
+  int ldr;
+  int act;
+  int out_fp32;
+  int rows_per_group, group_stride, group_offset;
+  const float* row_add;
+};
+
+// Grouped rasterisation: consecutive tile ids walk 8 M-tiles before moving to the next N-tile, so the CTAs
+// resident at one time share few W panels and few A panels (both stay L2-resident).
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  constexpr int G = 8;
+  const int per_group = G * tiles_n;
+  const int g = tile / per_group;
+  const int first_m = g * G;
+  const int gsize = min(G, tiles_m - first_m);
+  const int r = tile - g * per_group;
+  tm = first_m + r % gsize;
+  tn = r / gsize;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = args.tiles_m * args.tiles_n;
+  const int nkb = (args.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tm, tn;
+        decode_tile(tile, args.tiles_m, args.tiles_n, tm, tn);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+          tma_load_2d(sA + stage * C::kABytes, &tmA, &full[stage], kb * BK, tm * BM);
+          tma_load_2d(sB + stage * C::kBBytes, &tmB, &full[stage], kb * BK, tn * BN);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * C::kABytes));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // two warps per quarter split the column chunks
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool swiglu = args.act == ACT_SWIGLU;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tm, tn;
+      decode_tile(tile, args.tiles_m, args.tiles_n, tm, tn);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = tm * BM + quarter * 32 + lane;
+      const bool row_ok = row < args.M;
+      long out_row = row;
+      int grp_row = 0;
+      if (args.rows_per_group > 0) {
+        grp_row = row % args.rows_per_group;
+        out_row = (long)(row / args.rows_per_group) * args.group_stride + grp_row + args.group_offset;
+      }
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        const int col0 = tn * BN + chunk * 32;
+        if (col0 >= args.N) continue;  // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (args.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < args.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + j));
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+        }
+        if (swiglu) {
+          // (gate, up) interleaved: 32 accumulator columns -> 16 outputs
+          if (row_ok) {
+            const int ocol0 = col0 >> 1;
+            bf16* orow = reinterpret_cast<bf16*>(args.out) + out_row * args.ldo + ocol0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+              if (ocol0 + j < (args.N >> 1)) {
+                uint4 pk;
+                pk.x = pack_bf16(silu(v[2 * j + 0]) * v[2 * j + 1], silu(v[2 * j + 2]) * v[2 * j + 3]);
+                pk.y = pack_bf16(silu(v[2 * j + 4]) * v[2 * j + 5], silu(v[2 * j + 6]) * v[2 * j + 7]);
+                pk.z = pack_bf16(silu(v[2 * j + 8]) * v[2 * j + 9], silu(v[2 * j + 10]) * v[2 * j + 11]);
+                pk.w = pack_bf16(silu(v[2 * j + 12]) * v[2 * j + 13], silu(v[2 * j + 14]) * v[2 * j + 15]);
+                *reinterpret_cast<uint4*>(orow + j) = pk;
+              }
+            }
+          }
+          continue;
+        }
+        if (args.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (args.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (args.gamma) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < args.N) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(args.gamma + col0 + j));
+              v[j] *= g.x, v[j + 1] *= g.y, v[j + 2] *= g.z, v[j + 3] *= g.w;
+            }
+          }
+        }
+        if (row_ok) {
+        if (args.row_add) {
+          const float* ra = args.row_add + (long)grp_row * args.N + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < args.N) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(ra + j));
+              v[j] += a.x, v[j + 1] += a.y, v[j + 2] += a.z, v[j + 3] += a.w;
+            }
+          }
+        }
+        if (args.residual) {
+          const bf16* rr = args.residual + out_row * args.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < args.N) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rr + j));
+              v[j + 0] += bf16_lo(q.x), v[j + 1] += bf16_hi(q.x);
+              v[j + 2] += bf16_lo(q.y), v[j + 3] += bf16_hi(q.y);
+              v[j + 4] += bf16_lo(q.z), v[j + 5] += bf16_hi(q.z);
+              v[j + 6] += bf16_lo(q.w), v[j + 7] += bf16_hi(q.w);
+            }
+          }
+        }
+        if (args.out_fp32) {
+          float* orow = reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < args.N)
+              *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          bf16* orow = reinterpret_cast<bf16*>(args.out) + out_row * args.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < args.N) {
+              uint4 pk;
+              pk.x = pack_bf16(v[j + 0], v[j + 1]);
+              pk.y = pack_bf16(v[j + 2], v[j + 3]);
+              pk.z = pack_bf16(v[j + 4], v[j + 5]);
+              pk.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(orow + j) = pk;
+            }
+          }
+        }
+        }  // row_ok
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) throw Error(-4, "cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = [box_rows, 64].
+CUtensorMap make_map(const bf16* ptr, long rows, long cols, long ld, int box_rows) {
+  N1_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand not 16-byte aligned");
+  N1_CHECK(ld % 8 == 0, "GEMM operand leading dimension must be a multiple of 8 elements");
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-5, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return m;
+}
+
+template <int BN>
+void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  });
+  a.tiles_m = (M + BM - 1) / BM;
+  a.tiles_n = (N + BN - 1) / BN;
+  CUtensorMap tmA = make_map(A, M, K, lda, BM);
+  CUtensorMap tmB = make_map(W, N, K, ldw, BN);
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  N1_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+int device_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldo, int M, int N, int K,
+               const GemmEpilogue& e, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return;
+  N1_CHECK(K > 0 && K % 8 == 0, "GEMM K must be a positive multiple of 8");
+  N1_CHECK(N % 8 == 0, "GEMM N must be a multiple of 8 (pad the packed weight)");
+  N1_CHECK(!(e.act == ACT_SWIGLU) || N % 16 == 0, "SwiGLU GEMM needs N % 16 == 0");
+  GemmArgs a;
+  a.M = M, a.N = N, a.K = K;
+  a.out = out, a.ldo = ldo;
+  a.bias = e.bias, a.gamma = e.gamma, a.residual = e.residual, a.ldr = e.ldr;
+  a.act = e.act, a.out_fp32 = e.out_fp32;
+  a.rows_per_group = e.rows_per_group, a.group_stride = e.group_stride, a.group_offset = e.group_offset;
+  a.row_add = e.row_add;
+  // Tile-width choice: fewest waves first, then the widest tile (fewer A re-reads, longer MMA bursts).
+  const int sms = device_sm_count();
+  const int tm = (M + BM - 1) / BM;
+  auto cost = [&](int bn) {
+    const long tiles = (long)tm * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    return waves * (bn + 48);  // per-tile time ~ BN plus a fixed prologue/epilogue share
+  };
+  int bn = 256;
+  long best = cost(256);
+  if (cost(128) < best) best = cost(128), bn = 128;
+  if (cost(64) < best) bn = 64;
+  if (bn == 256)
+    launch<256>(A, lda, W, ldw, M, N, K, a, stream);
+  else if (bn == 128)
+    launch<128>(A, lda, W, ldw, M, N, K, a, stream);
+  else
+    launch<64>(A, lda, W, ldw, M, N, K, a, stream);
+}
+
+}  // namespace n1

@@ -1,0 +1,81 @@
+// Internal C++ interface between the model executors and the kernel launchers (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace n1 {
+
+typedef __nv_bfloat16 bf16;
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define N1_CHECK(cond, msg)                                                                       \
+  do {                                                                                            \
+    if (!(cond)) throw ::n1::Error(-2, std::string(__FILE__) + ":" + std::to_string(__LINE__) + \
+                                           ": " + (msg));                                         \
+  } while (0)
+
+#define N1_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw ::n1::Error(-3, std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + #call + \
+                                ": " + cudaGetErrorString(e__));                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------- GEMM
+// out[M, N'] = epilogue(A[M,K] @ W[N,K]^T).  A and W are bf16, K-major (row-major with leading
+// dimensions lda / ldw in elements, multiples of 8).  Accumulation in fp32 (TMEM).
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N]
+  const float* gamma = nullptr;     // [N]   layer-scale applied to (acc + bias) after activation
+  const bf16* residual = nullptr;   // [M, ldr] added last
+  int ldr = 0;
+  int act = ACT_NONE;               // ACT_SWIGLU: W rows interleaved (gate_j, up_j); N' = N / 2
+  int out_fp32 = 0;                 // write fp32 instead of bf16
+  // optional row remap of the OUTPUT (used to drop a patch-GEMM straight into a [n, 1+P, D] token buffer):
+  // out_row = (row / rows_per_group) * group_stride + row % rows_per_group + group_offset
+  int rows_per_group = 0, group_stride = 0, group_offset = 0;
+  const float* row_add = nullptr;   // [rows_per_group, N] fp32 added per (row % rows_per_group) (pos-embed)
+};
+
+void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldo, int M, int N, int K,
+               const GemmEpilogue& epi, cudaStream_t stream);
+
+int device_sm_count();
+
+// ------------------------------------------------------------------------------------------- norms
+// y = LayerNorm(x) * w + b  (rms=0)   or   y = x / rms(x) * w  (rms=1);  one warp per row; D % 8 == 0.
+void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const float* b, int rows, int D,
+               float eps, int rms, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- attention
+struct AttnParams {
+  const bf16* q;  // element (row, head, d) at q[row * ldq + head * hd + d]
+  const bf16* k;
+  const bf16* v;
+  bf16* o;
+  int ldq, ldk, ldv, ldo;
+  int heads_q, heads_kv, hd;
+  int batch;             // number of query sequences
+  int seq_q, seq_k;      // fixed lengths when cu_seqlens_* are null
+  const int* cu_q;       // [batch + 1] int32 device, optional (varlen)
+  const int* cu_k;       // [batch_kv + 1]
+  int kv_div;            // query sequence b reads kv sequence b / kv_div (>= 1)
+  int causal;            // bottom-right aligned causal mask (key j visible to query i iff j <= i + seq_k - seq_q)
+  float scale;
+  int max_seq_q;         // upper bound on query length (grid sizing) when varlen
+};
+void attention(const AttnParams& p, cudaStream_t stream);
+
+}  // namespace n1
