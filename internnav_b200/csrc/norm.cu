@@ -79,15 +79,17 @@ void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const f
                int rms, cudaStream_t stream) {
   if (rows <= 0) return;
   N1_CHECK(D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "norm: D and leading dims must be multiples of 8");
-  N1_CHECK(D <= 8 * 32 * 16, "norm: D too large");
+  N1_CHECK(D <= 8 * 32 * 20, "norm: D too large");
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
   if (D <= 8 * 32 * 2)
     norm_kernel<2><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
   else if (D <= 8 * 32 * 6)
     norm_kernel<6><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
+  else if (D <= 8 * 32 * 14)
+    norm_kernel<14><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
   else
-    norm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
+    norm_kernel<20><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
   N1_CUDA(cudaGetLastError());
 }
 

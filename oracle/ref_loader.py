@@ -1,0 +1,109 @@
+"""Import the REFERENCE's own NavDP / DINOv2 modules from /root/reference (this container only).
+
+TEST INFRASTRUCTURE.  Used by oracle/gen_golden.py to produce tests/golden/*.npz and by
+tests/test_oracle_vs_reference.py to pin the restatement in oracle/navdp_oracle.py.  /root/reference does not exist
+on the GPU box, so nothing that runs there imports this module.
+
+Three shims:
+  1. `internnav.model.encoder` is registered as a bare package so its __init__ (-> bert_backbone -> transformers<5
+     internals) is skipped;
+  2. `diffusers.schedulers.scheduling_ddpm.DDPMScheduler` is absent from the image: oracle.ddpm.DDPMScheduler (a
+     restatement of diffusers==0.33.1, requirements/internvla_n1.txt L3) is injected -- so the DDPM arithmetic (row a10)
+     is NOT pinned by the reference, only its call sites (navdp.py L74-76, L173, L247-250) are;
+  3. DAT_RGBD_Patch_Backbone.__init__ torch.load()s a checkpoint unconditionally (navdp_backbone.py L124): torch.load
+     is patched to return {} during construction (load_state_dict(strict=False) then keeps the random init).
+"""
+import importlib
+import os
+import sys
+import types
+
+REF = os.environ.get("N1_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "internnav", "model"))
+
+
+def _bare_package(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    m.__package__ = name
+    sys.modules[name] = m
+    return m
+
+
+def load_reference_navdp():
+    """Returns the reference module internnav.model.basemodel.internvla_n1.navdp (classes untouched)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+    from . import ddpm
+
+    if "internnav" not in sys.modules:
+        _bare_package("internnav", os.path.join(REF, "internnav"))
+        _bare_package("internnav.model", os.path.join(REF, "internnav", "model"))
+        _bare_package("internnav.model.encoder", os.path.join(REF, "internnav", "model", "encoder"))
+        _bare_package("internnav.model.basemodel", os.path.join(REF, "internnav", "model", "basemodel"))
+        _bare_package("internnav.model.basemodel.internvla_n1",
+                      os.path.join(REF, "internnav", "model", "basemodel", "internvla_n1"))
+    if "diffusers" not in sys.modules:
+        d = types.ModuleType("diffusers")
+        ds = types.ModuleType("diffusers.schedulers")
+        dd = types.ModuleType("diffusers.schedulers.scheduling_ddpm")
+        dd.DDPMScheduler = ddpm.DDPMScheduler
+        ds.scheduling_ddpm = dd
+        d.schedulers = ds
+        sys.modules.update({"diffusers": d, "diffusers.schedulers": ds, "diffusers.schedulers.scheduling_ddpm": dd})
+    tp = os.path.join(REF, "third_party", "diffusion-policy")
+    if tp not in sys.path:
+        sys.path.insert(0, tp)
+    if "diffusion_policy" not in sys.modules and not os.path.isdir(os.path.join(tp, "diffusion_policy")):
+        # un-checked-out submodule: the only symbol used is SinusoidalPosEmb, which navdp_backbone's star import
+        # shadows anyway
+        dp = types.ModuleType("diffusion_policy")
+        dpm = types.ModuleType("diffusion_policy.model")
+        dpd = types.ModuleType("diffusion_policy.model.diffusion")
+        dpp = types.ModuleType("diffusion_policy.model.diffusion.positional_embedding")
+        dpp.SinusoidalPosEmb = object
+        sys.modules.update({"diffusion_policy": dp, "diffusion_policy.model": dpm,
+                            "diffusion_policy.model.diffusion": dpd,
+                            "diffusion_policy.model.diffusion.positional_embedding": dpp})
+    return importlib.import_module("internnav.model.basemodel.internvla_n1.navdp")
+
+
+def build_reference_navdp(predict_size=32, memory_size=2, navdp_version=0.1):
+    """Construct the reference NavDP_Policy_DPT_CriticSum_DAT in fp32 on CPU (random init)."""
+    import torch
+
+    mod = load_reference_navdp()
+    real_load = torch.load
+    torch.load = lambda *a, **k: {}
+    try:
+        m = mod.NavDP_Policy_DPT_CriticSum_DAT(memory_size=memory_size, predict_size=predict_size,
+                                               navdp_version=navdp_version, input_dtype="fp32", device="cpu")
+    finally:
+        torch.load = real_load
+    m.rgbd_encoder.input_dtype = torch.float32
+    m.rgbd_encoder.preprocess_mean = m.rgbd_encoder.preprocess_mean.float()
+    m.rgbd_encoder.preprocess_std = m.rgbd_encoder.preprocess_std.float()
+    return m.eval()
+
+
+def load_reference_vln_utils():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "_ref_vln_utils", os.path.join(REF, "internnav", "model", "utils", "vln_utils.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def load_reference_rope2d():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "_ref_rope2d", os.path.join(REF, "internnav", "dataset", "rope2d.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
