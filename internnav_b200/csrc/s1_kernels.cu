@@ -20,8 +20,9 @@ __global__ void patchify_rgb_kernel(const float* __restrict__ img, bf16* __restr
   if (col < 588) {
     const int c = col / 196, k = col % 196, ky = k / 14, kx = k % 14;
     const int im = row / 256, p = row % 256, py = p / 16, px = p % 16;
-    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    // bf16 roundings of the ImageNet mean/std: the reference holds these constants in bf16 (navdp_backbone.py L126-127)
+    const float mean = c == 0 ? 0.484375f : (c == 1 ? 0.455078125f : 0.40625f);
+    const float stdv = c == 0 ? 0.228515625f : (c == 1 ? 0.2236328125f : 0.224609375f);
     const float x = img[(((long)im * 224 + py * 14 + ky) * 224 + px * 14 + kx) * 3 + c];
     v = (x - mean) / stdv;
   }
