@@ -52,6 +52,9 @@ SYMBOLS = {
     "n1_navdp_sample": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_void_p]),
     "n1_ddpm_tables": (c_int, [c_int, ctypes.POINTER(c_float)]),
+    "n1_prof_enable": (None, [c_int]),
+    "n1_prof_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
@@ -104,6 +107,18 @@ def dtype_code(t):
     if t.dtype == torch.bfloat16:
         return 1
     raise TypeError("n1b200 takes fp32 or bf16 tensors, got %s" % t.dtype)
+
+
+def prof_enable(on):
+    lib().n1_prof_enable(1 if on else 0)
+
+
+def prof_read():
+    """-> dict(gemm_ms, gemm_flops, gemm_launches, total_launches) since the last read."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    c, d = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().n1_prof_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+    return {"gemm_ms": a.value, "gemm_flops": b.value, "gemm_launches": c.value, "total_launches": d.value}
 
 
 # ------------------------------------------------------------------------------------------ kernel-level ops

@@ -171,6 +171,18 @@ int n1_ddpm_tables(int K, float* out_host) {
   });
 }
 
+void n1_prof_enable(int on) { prof_enable(on != 0); }
+
+int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* total_launches) {
+  return guard([&] {
+    ProfStats st = prof_read_and_reset();
+    if (gemm_ms) *gemm_ms = st.gemm_ms;
+    if (gemm_flops) *gemm_flops = st.gemm_flops;
+    if (gemm_launches) *gemm_launches = st.gemm_launches;
+    if (total_launches) *total_launches = st.total_launches;
+  });
+}
+
 int n1_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                const float* bias, const float* gamma, const void* residual, int ldr, int act, int out_fp32,
                void* stream) {

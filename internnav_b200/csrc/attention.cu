@@ -238,6 +238,7 @@ void launch_attn(const AttnParams& p, cudaStream_t stream) {
   const int maxq = p.cu_q ? p.max_seq_q : p.seq_q;
   dim3 grid((maxq + BQ - 1) / BQ, p.heads_q, p.batch);
   attn_kernel<HD><<<grid, 128, C::kSmemBytes, stream>>>(p);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 

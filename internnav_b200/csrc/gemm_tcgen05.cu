@@ -9,7 +9,9 @@
 // This one kernel carries every Linear / Conv-as-GEMM on the InternVLA-N1 hot path:
 // the reference reaches cuBLAS through nn.Linear at navdp.py L57-66/L94-100, navdp_backbone.py L147-149,
 // dinov2_layers/{attention.py L46-48, mlp.py L30-32, patch_embed.py L65} and the Qwen2.5-VL blocks.
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "n1_ops.h"
 #include "n1_ptx.cuh"
@@ -350,7 +352,35 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   N1_CUDA(cudaGetLastError());
 }
 
+// ---- profiling state
+std::atomic<long> g_total_launches{0}, g_gemm_launches{0};
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+struct EvPair {
+  cudaEvent_t a, b;
+  double flops;
+};
+std::vector<EvPair> g_events;
+
 }  // namespace
+
+void prof_enable(bool on) { g_prof_on = on; }
+void prof_count_launch(int n) { g_total_launches += n; }
+ProfStats prof_read_and_reset() {
+  ProfStats st;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (EvPair& e : g_events) {
+    cudaEventSynchronize(e.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) st.gemm_ms += ms, st.gemm_flops += e.flops;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_events.clear();
+  st.gemm_launches = g_gemm_launches.exchange(0);
+  st.total_launches = g_total_launches.exchange(0);
+  return st;
+}
 
 int device_sm_count() {
   static int sms = 0;
@@ -384,6 +414,16 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
     const long waves = (tiles + sms - 1) / sms;
     return waves * (bn + 48);  // per-tile time ~ BN plus a fixed prologue/epilogue share
   };
+  EvPair ev{};
+  const bool prof = g_prof_on.load();
+  if (prof) {
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    ev.flops = 2.0 * M * (double)N * K;
+    cudaEventRecord(ev.a, stream);
+  }
+  g_gemm_launches++;
+  g_total_launches++;
   int bn = 256;
   long best = cost(256);
   if (cost(128) < best) best = cost(128), bn = 128;
@@ -394,6 +434,11 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
     launch<128>(A, lda, W, ldw, M, N, K, a, stream);
   else
     launch<64>(A, lda, W, ldw, M, N, K, a, stream);
+  if (prof) {
+    cudaEventRecord(ev.b, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_events.push_back(ev);
+  }
 }
 
 }  // namespace n1

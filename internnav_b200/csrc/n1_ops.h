@@ -54,6 +54,15 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
 
 int device_sm_count();
 
+// Launch accounting (always on) and optional per-GEMM event timing (bench.py's roofline pass).
+struct ProfStats {
+  double gemm_ms = 0, gemm_flops = 0;
+  long gemm_launches = 0, total_launches = 0;
+};
+void prof_enable(bool on);
+void prof_count_launch(int n = 1);
+ProfStats prof_read_and_reset();
+
 // ------------------------------------------------------------------------------------------- norms
 // y = LayerNorm(x) * w + b  (rms=0)   or   y = x / rms(x) * w  (rms=1);  one warp per row; D % 8 == 0.
 void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const float* b, int rows, int D,

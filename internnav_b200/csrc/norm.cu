@@ -90,6 +90,7 @@ void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const f
     norm_kernel<14><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
   else
     norm_kernel<20><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 

@@ -213,48 +213,58 @@ inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
 void patchify_rgb(const float* img, bf16* out, int n_img, int ldk, cudaStream_t s) {
   const long total = (long)n_img * 256 * ldk;
   patchify_rgb_kernel<<<nblk(total, 256), 256, 0, s>>>(img, out, n_img, ldk);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void patchify_depth(const float* img, bf16* out, int n_img, int ldk, cudaStream_t s) {
   const long total = (long)n_img * 256 * ldk;
   patchify_depth_kernel<<<nblk(total, 256), 256, 0, s>>>(img, out, n_img, ldk);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void fill_cls(bf16* x, const float* cls_pos, int n_img, int tokens, int D, cudaStream_t s) {
   fill_cls_kernel<<<nblk((long)n_img * D, 256), 256, 0, s>>>(x, cls_pos, n_img, tokens, D);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void vit_out(const bf16* x, bf16* mem, const float* w, const float* b, const float* pe, int n_img, int frames,
              int slot_base, int slots, cudaStream_t s) {
   vit_out_kernel<<<nblk((long)n_img * 256 * 32, 256), 256, 0, s>>>(x, mem, w, b, pe, n_img, frames, slot_base, slots);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void bcast_rows(const bf16* src, bf16* dst, long rows, int period, int D, cudaStream_t s) {
   bcast_rows_kernel<<<nblk(rows * D / 8, 256), 256, 0, s>>>(src, dst, rows, period, D);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void embed_actions(const float* xt, const float* w, const float* bias, const float* pos, bf16* tgt, long rows, int T,
                    cudaStream_t s) {
   embed_actions_kernel<<<nblk(rows * 192, 256), 256, 0, s>>>(xt, w, bias, pos, tgt, rows, T);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void build_cond(const int* tsteps, int t_scalar, const bf16* goal, const bf16* rgbd, const float* cpe, bf16* cond, int B,
                 int Mtok, int first_slot, int num_slots, cudaStream_t s) {
   build_cond_kernel<<<nblk((long)B * num_slots * 384, 256), 256, 0, s>>>(tsteps, t_scalar, goal, rgbd, cpe, cond, B, Mtok,
                                                                         first_slot, num_slots);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void head_ddpm(const bf16* h, const float* lw, const float* lb, const float* hw, const float* hb, long rows, int mode,
                float* x, const float* noise, float* eps_out, const DdpmCoef& cf, cudaStream_t s) {
   head_kernel<<<nblk(rows * 32, 256), 256, 0, s>>>(h, lw, lb, hw, hb, rows, mode, x, noise, eps_out, cf);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
   f32_to_bf16_kernel<<<nblk(n, 256), 256, 0, s>>>(src, dst, n);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s) {
   bf16_to_f32_kernel<<<nblk(n, 256), 256, 0, s>>>(src, dst, n);
+  prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 

@@ -1,0 +1,91 @@
+"""Parameter manifest of the System-1 head: names and shapes exactly as `NavDP_Policy_DPT_CriticSum_DAT.state_dict()`
+produces them in the reference (navdp.py L16-114), generated from the dimensions -- so the mirror
+class can be random-initialised, checkpointed and handed to an optimiser without the reference installed.
+tests/test_manifest.py checks it against the manifest dumped from the reference class itself.
+"""
+from collections import OrderedDict
+
+import torch
+
+
+def _mha(p, D):
+    return [(p + "in_proj_weight", (3 * D, D)), (p + "in_proj_bias", (3 * D,)), (p + "out_proj.weight", (D, D)),
+            (p + "out_proj.bias", (D,))]
+
+
+def _dec_layer(p, D, ff):
+    out = _mha(p + "self_attn.", D) + _mha(p + "multihead_attn.", D)
+    out += [(p + "linear1.weight", (ff, D)), (p + "linear1.bias", (ff,)), (p + "linear2.weight", (D, ff)),
+            (p + "linear2.bias", (D,))]
+    for n in ("norm1", "norm2", "norm3"):
+        out += [(p + n + ".weight", (D,)), (p + n + ".bias", (D,))]
+    return out
+
+
+def _vit(p, D=384, depth=12, grid=37):
+    out = [(p + "cls_token", (1, 1, D)), (p + "pos_embed", (1, grid * grid + 1, D)), (p + "mask_token", (1, D)),
+           (p + "patch_embed.proj.weight", (D, 3, 14, 14)), (p + "patch_embed.proj.bias", (D,))]
+    for i in range(depth):
+        b = "%sblocks.%d." % (p, i)
+        out += [(b + "norm1.weight", (D,)), (b + "norm1.bias", (D,)), (b + "attn.qkv.weight", (3 * D, D)),
+                (b + "attn.qkv.bias", (3 * D,)), (b + "attn.proj.weight", (D, D)), (b + "attn.proj.bias", (D,)),
+                (b + "ls1.gamma", (D,)), (b + "norm2.weight", (D,)), (b + "norm2.bias", (D,)),
+                (b + "mlp.fc1.weight", (4 * D, D)), (b + "mlp.fc1.bias", (4 * D,)), (b + "mlp.fc2.weight", (D, 4 * D)),
+                (b + "mlp.fc2.bias", (D,)), (b + "ls2.gamma", (D,))]
+    out += [(p + "norm.weight", (D,)), (p + "norm.bias", (D,))]
+    return out
+
+
+def navdp_shapes(memory_size=2, predict_size=32, temporal_depth=16, token_dim=384, vlm_token_dim=3584,
+                 navdp_version=0.1):
+    D = token_dim
+    items = [("cond_pos_embed", (1, memory_size * 16 + 2, D)), ("out_pos_embed", (1, predict_size, D))]
+    items += _vit("rgbd_encoder.rgb_model.") + _vit("rgbd_encoder.depth_model.")
+    pe_rows = (memory_size * 2) * 256 if navdp_version > 0.0 else (memory_size + 1) * 256
+    items += [("rgbd_encoder.former_query.weight", (memory_size * 16, D)), ("rgbd_encoder.former_pe.weight", (pe_rows, D))]
+    for i in range(2):
+        items += _dec_layer("rgbd_encoder.former_net.layers.%d." % i, D, 2048)
+    items += [("rgbd_encoder.project_layer.weight", (D, D)), ("rgbd_encoder.project_layer.bias", (D,)),
+              ("point_encoder.weight", (D, 3)), ("point_encoder.bias", (D,))]
+    items += _dec_layer("decoder_layer.", D, 4 * D)
+    for i in range(temporal_depth):
+        items += _dec_layer("decoder.layers.%d." % i, D, 4 * D)
+    items += [("input_embed.weight", (D, 3)), ("input_embed.bias", (D,)), ("layernorm.weight", (D,)),
+              ("layernorm.bias", (D,)), ("action_head.weight", (3, D)), ("action_head.bias", (3,)),
+              ("critic_head.weight", (1, D)), ("critic_head.bias", (1,))]
+    v = vlm_token_dim
+    for idx, (o, i) in zip((0, 2, 4), ((v // 4, v), (v // 8, v // 4), (D, v // 8))):
+        items += [("vlm_embed_mlp.%d.weight" % idx, (o, i)), ("vlm_embed_mlp.%d.bias" % idx, (o,))]
+    g = "goal_compressor."
+    items += [(g + "target_embedding.weight", (1, D)), (g + "positional_encoding.pe", (1000, D)),
+              (g + "token_positional_encoding.position_embedding.weight", (5000, D)),
+              (g + "query_positional_encoding.position_embedding.weight", (5000, D))]
+    items += _mha(g + "cross_attention.", D)
+    for idx, (o, i) in zip((0, 2), ((D // 2, 2), (D, D // 2))):
+        items += [("pg_embed_mlp.%d.weight" % idx, (o, i)), ("pg_embed_mlp.%d.bias" % idx, (o,))]
+    for idx, (o, i) in zip((0, 2, 4), ((D // 2, D), (D // 4, D // 2), (2, D // 4))):
+        items += [("pg_pred_mlp.%d.weight" % idx, (o, i)), ("pg_pred_mlp.%d.bias" % idx, (o,))]
+    return OrderedDict(items)
+
+
+def random_navdp_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
+    """Random weights of the right shapes (synthetic benchmark / smoke runs; there are no checkpoints offline).
+    Scales keep activations O(1); tables the reference zero-initialises get small non-zero values."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = OrderedDict()
+    for name, shape in navdp_shapes(**dims).items():
+        last = name.split(".")[-1]
+        if (("norm" in name and last == "weight") or last == "gamma") and len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) >= 2 and last not in ("pe",) and "embed" not in last and "token" not in last and "former" not in name \
+                and "position_embedding" not in name and "target_embedding" not in name:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) / fan_in ** 0.5
+        elif len(shape) >= 2:
+            t = 0.1 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        out[name] = t.to(device=device, dtype=dtype)
+    return out
