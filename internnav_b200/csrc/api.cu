@@ -6,6 +6,7 @@
 #include "../../include/n1b200.h"
 #include "n1_ops.h"
 #include "s1_model.h"
+#include "s2_model.h"
 #include "weights.h"
 
 using namespace n1;
@@ -13,6 +14,13 @@ using namespace n1;
 struct n1_ctx {
   int device = 0;
   S1Model s1;
+  S2Model s2;
+};
+struct n1_vit_plan_s {
+  VitPlan* p;
+};
+struct n1_llm_plan_s {
+  LlmPlan* p;
 };
 
 namespace {
@@ -168,6 +176,132 @@ int n1_ddpm_tables(int K, float* out_host) {
       out_host[i * 5 + 0] = c[i].sqrt_one_minus_acp, out_host[i * 5 + 1] = c[i].inv_sqrt_acp;
       out_host[i * 5 + 2] = c[i].c0, out_host[i * 5 + 3] = c[i].c1, out_host[i * 5 + 4] = c[i].sigma;
     }
+  });
+}
+
+int n1_s2_load(n1_handle h, const n1_s2_dims* d, const n1_tensor_desc* tensors, int n, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!d || !tensors || n <= 0) throw Error(N1_ERR_ARG, "n1_s2_load: null dims/tensors");
+    S2Dims x;
+    x.v_depth = d->v_depth, x.v_hidden = d->v_hidden, x.v_heads = d->v_heads, x.v_inter = d->v_inter;
+    x.v_patch = d->v_patch, x.v_tpatch = d->v_tpatch, x.v_merge = d->v_merge, x.v_window = d->v_window, x.v_out = d->v_out;
+    x.n_fullatt = d->n_fullatt;
+    if (x.n_fullatt < 0 || x.n_fullatt > 16) throw Error(N1_ERR_ARG, "n_fullatt out of range");
+    for (int i = 0; i < 16; ++i) x.fullatt[i] = d->fullatt[i];
+    x.layers = d->layers, x.hidden = d->hidden, x.heads = d->heads, x.kv_heads = d->kv_heads, x.head_dim = d->head_dim;
+    x.inter = d->inter, x.vocab = d->vocab, x.rms_eps = d->rms_eps, x.rope_theta = d->rope_theta;
+    for (int i = 0; i < 3; ++i) x.mrope[i] = d->mrope[i];
+    x.n_query = d->n_query;
+    h->s2.load(to_source(tensors, n), x, S(stream));
+  });
+}
+
+int n1_vit_plan_create(n1_handle h, const int32_t* grid, int n_img, n1_vit_plan* out, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!grid || n_img <= 0 || !out) throw Error(N1_ERR_ARG, "n1_vit_plan_create: bad arguments");
+    n1_vit_plan_s* w = new n1_vit_plan_s();
+    try {
+      w->p = h->s2.make_vit_plan(grid, n_img, S(stream));
+    } catch (...) {
+      delete w;
+      throw;
+    }
+    *out = w;
+  });
+}
+void n1_vit_plan_destroy(n1_vit_plan p) {
+  if (!p) return;
+  delete p->p;
+  delete p;
+}
+int64_t n1_vit_plan_patches(n1_vit_plan p) { return p ? p->p->host.n_patches : 0; }
+
+int n1_llm_plan_create(n1_handle h, const int32_t* ids, const int32_t* lens, int B, const int32_t* grid, int n_img,
+                       n1_llm_plan* out, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!ids || !lens || B <= 0 || !out) throw Error(N1_ERR_ARG, "n1_llm_plan_create: bad arguments");
+    n1_llm_plan_s* w = new n1_llm_plan_s();
+    try {
+      w->p = h->s2.make_llm_plan(ids, lens, B, grid, n_img, S(stream));
+    } catch (...) {
+      delete w;
+      throw;
+    }
+    *out = w;
+  });
+}
+void n1_llm_plan_destroy(n1_llm_plan p) {
+  if (!p) return;
+  delete p->p;
+  delete p;
+}
+int64_t n1_llm_plan_tokens(n1_llm_plan p) { return p ? p->p->tokens : 0; }
+int64_t n1_llm_plan_image_tokens(n1_llm_plan p) { return p ? p->p->n_image_tokens : 0; }
+int n1_llm_plan_positions(n1_llm_plan p, int32_t* pos3, int32_t* delta) {
+  return guard([&] {
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    if (pos3) memcpy(pos3, p->p->h_pos3.data(), p->p->h_pos3.size() * sizeof(int32_t));
+    if (delta) memcpy(delta, p->p->h_delta.data(), p->p->h_delta.size() * sizeof(int32_t));
+  });
+}
+
+size_t n1_vit_workspace_bytes(n1_handle h, n1_vit_plan p) {
+  size_t r = 0;
+  guard([&] {
+    if (!h || !p) throw Error(N1_ERR_ARG, "null handle/plan");
+    r = h->s2.ws_vit(*p->p);
+  });
+  return r;
+}
+size_t n1_llm_workspace_bytes(n1_handle h, n1_llm_plan p) {
+  size_t r = 0;
+  guard([&] {
+    if (!h || !p) throw Error(N1_ERR_ARG, "null handle/plan");
+    r = h->s2.ws_llm(*p->p);
+  });
+  return r;
+}
+
+int n1_qwen_vit(n1_handle h, n1_vit_plan p, void* ws, size_t ws_bytes, const void* pixels, void* out, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    h->s2.vit_forward(*p->p, ws, ws_bytes, B16(pixels), B16(out), S(stream));
+  });
+}
+int n1_llm_prefill(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* image_feats, void* latents,
+                   void* stream) {
+  return guard([&] {
+    use(h);
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    h->s2.llm_prefill(*p->p, ws, ws_bytes, B16(image_feats), B16(latents), S(stream));
+  });
+}
+
+int n1_rope_index(const int32_t* ids, int len, const int32_t* grid, int n_img, int merge, int32_t* pos3,
+                  int32_t* delta) {
+  return guard([&] {
+    if (!ids || len <= 0 || !pos3) throw Error(N1_ERR_ARG, "n1_rope_index: bad arguments");
+    std::vector<int> p;
+    int cursor = 0, d = 0;
+    rope_index_one(ids, len, grid, n_img, merge, cursor, p, d);
+    memcpy(pos3, p.data(), p.size() * sizeof(int32_t));
+    if (delta) *delta = d;
+  });
+}
+int n1_vit_window_index(const int32_t* grid, int n_img, int merge, int window, int32_t* widx, int32_t* cu, int32_t* n_cu,
+                        int32_t* pos_hw) {
+  return guard([&] {
+    if (!grid || n_img <= 0) throw Error(N1_ERR_ARG, "n1_vit_window_index: bad arguments");
+    VitIndex v;
+    vit_index(grid, n_img, merge, window, v);
+    if (widx) memcpy(widx, v.window_index.data(), v.window_index.size() * sizeof(int32_t));
+    if (cu) memcpy(cu, v.cu_window.data(), v.cu_window.size() * sizeof(int32_t));
+    if (n_cu) *n_cu = (int32_t)v.cu_window.size();
+    if (pos_hw) memcpy(pos_hw, v.pos_hw.data(), v.pos_hw.size() * sizeof(int32_t));
   });
 }
 

@@ -1,0 +1,88 @@
+// System-2 executor: Qwen2.5-VL vision transformer and decoder prefill, sequenced from host C++ over the kernels in
+// this directory.  Replaces `self.visual(pixel_values, grid_thw)` and `self.model(inputs_embeds, position_ids)` as
+// called by InternVLAN1ForCausalLM.generate_latents (internvla_n1.py L320-347); the arithmetic itself lives in the
+// un-vendored pin transformers==4.51.0 (modeling_qwen2_5_vl.py) and is restated in oracle/qwen_oracle.py.
+#pragma once
+#include <vector>
+
+#include "s1_model.h"
+#include "s2_plan.h"
+
+namespace n1 {
+
+struct S2Dims {
+  // vision tower
+  int v_depth = 32, v_hidden = 1280, v_heads = 16, v_inter = 3420, v_patch = 14, v_tpatch = 2, v_merge = 2;
+  int v_window = 112, v_out = 3584;
+  int n_fullatt = 4, fullatt[16] = {7, 15, 23, 31};
+  // language model
+  int layers = 28, hidden = 3584, heads = 28, kv_heads = 4, head_dim = 128, inter = 18944, vocab = 152064;
+  float rms_eps = 1e-6f, rope_theta = 1000000.0f;
+  int mrope[3] = {16, 24, 24};
+  int n_query = 4;
+};
+
+// Device-resident index arrays for one batch of images (immutable; reusable across calls with the same grids).
+struct VitPlan {
+  VitIndex host;
+  int *window_index = nullptr, *reverse_index = nullptr, *cu_window = nullptr, *cu_full = nullptr;
+  float2* rope = nullptr;  // [n_patches, head_dim / 2] (cos, sin), window order
+  int n_window = 0, n_full = 0;
+  ~VitPlan();
+};
+
+// Device-resident token bookkeeping for one batch of prompts (generate_latents appends n_query TRAJ tokens each).
+struct LlmPlan {
+  int B = 0, max_len = 0, n_query = 0;
+  long tokens = 0, n_image_tokens = 0;
+  std::vector<int> h_cu, h_pos3, h_delta;
+  int *cu = nullptr, *kind = nullptr, *src = nullptr, *out_rows = nullptr;
+  float2* rope = nullptr;  // [tokens, head_dim / 2]
+  ~LlmPlan();
+};
+
+class S2Model {
+ public:
+  S2Dims dims;
+  void load(const WeightSource& ws, const S2Dims& d, cudaStream_t s);
+  bool loaded() const { return loaded_; }
+
+  VitPlan* make_vit_plan(const int32_t* grid_thw_host, int n_img, cudaStream_t s) const;
+  // ids: packed prompt token ids (host), lens[B]; TRAJ tokens are appended per sequence by the planner.
+  LlmPlan* make_llm_plan(const int32_t* ids_host, const int32_t* lens_host, int B, const int32_t* grid_thw_host,
+                         int n_img, cudaStream_t s) const;
+
+  size_t ws_vit(const VitPlan& p) const;
+  // pixels bf16 [n_patches, 3 * tpatch * patch^2] -> out bf16 [n_patches / merge^2, v_out] (original token order)
+  void vit_forward(const VitPlan& p, void* ws, size_t ws_bytes, const bf16* pixels, bf16* out, cudaStream_t s) const;
+  size_t ws_llm(const LlmPlan& p) const;
+  // image_feats bf16 [n_image_tokens, hidden] -> out bf16 [B, n_query, hidden] (final-norm states of the TRAJ rows)
+  void llm_prefill(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, bf16* out,
+                   cudaStream_t s) const;
+
+ private:
+  struct VBlock {
+    float *n1 = nullptr, *n2 = nullptr;
+    Lin qkv, proj, gateup, down;
+  };
+  struct LBlock {
+    float *n1 = nullptr, *n2 = nullptr;
+    Lin qkv, o, gateup, down;
+  };
+  size_t vit_impl(Carver c, const VitPlan& p, const bf16* pixels, bf16* out, cudaStream_t s) const;
+  size_t llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf16* out, cudaStream_t s) const;
+
+  Arena arena_;
+  bool loaded_ = false;
+  int v_inter_pad_ = 0, inter_pad_ = 0, patch_k_ = 0;
+  Lin v_patch_;
+  std::vector<VBlock> vblk_;
+  float* merger_ln_ = nullptr;
+  Lin merger0_, merger2_;
+  bf16* embed_ = nullptr;    // [vocab, hidden]
+  bf16* latentq_ = nullptr;  // [n_query, hidden]
+  std::vector<LBlock> lblk_;
+  float* final_norm_ = nullptr;
+};
+
+}  // namespace n1

@@ -1,0 +1,144 @@
+"""Pins the System-2 oracle (oracle/qwen_oracle.py) and the C++ integer planners -- CPU only.
+
+  * vision tower / decoder restatements vs the container's transformers implementation of the same Qwen2.5-VL blocks
+    (seeded tiny configs, fp32, eager attention);
+  * rope_index vs the reference's own internnav/dataset/rope2d.py (when /root/reference exists) and vs the committed
+    fixture tests/golden/rope_index.json (everywhere);
+  * libn1b200's host-only planners (n1_rope_index, n1_vit_window_index) bit-exact vs the oracle.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen_oracle as Q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "rope_index.json")
+
+
+def _cases():
+    rng = np.random.Generator(np.random.PCG64(7))
+    cases = []
+    for pre, grids, post in [(24, [(1, 28, 28)], 80), (5, [(1, 16, 16), (1, 16, 16)], 9), (0, [(1, 28, 20)], 1),
+                             (12, [(1, 8, 12), (1, 28, 28), (1, 4, 4)], 30), (40, [], 7),
+                             (3, [(1, 28, 28)] * 9, 60)]:
+        ids = Q.make_prompt(rng, pre, grids, post) + [Q.TRAJ_TOKEN_INDEX] * 4
+        cases.append((ids, [list(g) for g in grids]))
+    return cases
+
+
+def test_rope_index_golden():
+    with open(GOLD) as fh:
+        gold = json.load(fh)
+    for (ids, grids), g in zip(_cases(), gold):
+        assert ids == g["input_ids"]
+        pos, delta = Q.rope_index(torch.tensor([ids]), torch.tensor(grids).reshape(-1, 3))
+        assert pos[:, 0].tolist() == g["position_ids"] and int(delta) == g["delta"]
+
+
+def test_rope_index_vs_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    ref = ref_loader.load_reference_rope2d()
+    for ids, grids in _cases():
+        t = torch.tensor([ids])
+        g = torch.tensor(grids).reshape(-1, 3) if grids else None
+        rp, rd = ref.get_rope_index_25(2, t, g)
+        if g is None:
+            g = torch.zeros(0, 3, dtype=torch.long)
+        pos, delta = Q.rope_index(t, g)
+        assert torch.equal(rp, pos) and int(rd) == int(delta)
+
+
+def _lib():
+    from internnav_b200 import _lib
+    return _lib.lib()
+
+
+def test_cxx_rope_index_bit_exact():
+    L = _lib()
+    for ids, grids in _cases():
+        n = len(ids)
+        a = (ctypes.c_int32 * n)(*ids)
+        g = (ctypes.c_int32 * max(1, 3 * len(grids)))(*[v for gr in grids for v in gr])
+        out = (ctypes.c_int32 * (3 * n))()
+        d = ctypes.c_int32()
+        rc = L.n1_rope_index(a, n, g, len(grids), 2, out, ctypes.byref(d))
+        assert rc == 0, L.n1_last_error()
+        pos, delta = Q.rope_index(torch.tensor([ids]), torch.tensor(grids).reshape(-1, 3))
+        assert list(out) == pos[:, 0].reshape(-1).tolist() and d.value == int(delta)
+
+
+@pytest.mark.parametrize("grids", [[(1, 28, 28)], [(1, 16, 16), (1, 28, 20)], [(1, 8, 8)], [(2, 12, 20)],
+                                   [(1, 32, 32), (1, 4, 4), (1, 28, 28)]])
+def test_cxx_window_index_bit_exact(grids):
+    L = _lib()
+    n_p = sum(t * h * w for t, h, w in grids)
+    g = (ctypes.c_int32 * (3 * len(grids)))(*[v for gr in grids for v in gr])
+    widx = (ctypes.c_int32 * (n_p // 4))()
+    cu = (ctypes.c_int32 * (n_p // 4 + 2))()
+    ncu = ctypes.c_int32()
+    pos = (ctypes.c_int32 * (2 * n_p))()
+    assert L.n1_vit_window_index(g, len(grids), 2, 4, widx, cu, ctypes.byref(ncu), pos) == 0, L.n1_last_error()
+    pos_ids, window_index, cu_window, _ = Q.vit_indices(grids)
+    assert list(widx) == window_index.tolist()
+    assert list(cu)[: ncu.value] == cu_window.tolist()
+    reordered = pos_ids.reshape(n_p // 4, 4, 2)[window_index].reshape(-1).tolist()
+    assert list(pos) == reordered
+
+
+def _hf_cfgs(cfg):
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLTextConfig, Qwen2_5_VLVisionConfig
+    vc = Qwen2_5_VLVisionConfig(depth=cfg["v_depth"], hidden_size=cfg["v_hidden"], num_heads=cfg["v_heads"],
+                                intermediate_size=cfg["v_inter"], out_hidden_size=cfg["v_out"],
+                                fullatt_block_indexes=cfg["fullatt"], window_size=cfg["v_window"], hidden_act="silu")
+    tc = Qwen2_5_VLTextConfig(hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+                              num_attention_heads=cfg["heads"], num_key_value_heads=cfg["kv_heads"],
+                              intermediate_size=cfg["inter"], vocab_size=cfg["vocab"], rms_norm_eps=cfg["rms_eps"],
+                              rope_parameters={"rope_type": "default", "rope_theta": cfg["rope_theta"],
+                                               "mrope_section": cfg["mrope"]}, use_sliding_window=False)
+    return vc, tc
+
+
+def test_vision_tower_vs_transformers():
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel as VT
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=1, vocab_rows=64)
+    vc, _ = _hf_cfgs(cfg)
+    m = VT._from_config(vc, attn_implementation="eager").float().eval()
+    missing = m.load_state_dict({k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}, strict=True)
+    grids = [(1, 16, 20), (1, 28, 28)]
+    n_p = sum(t * h * w for t, h, w in grids)
+    torch.manual_seed(0)
+    px = torch.randn(n_p, 1176)
+    with torch.no_grad():
+        ref = m(px, grid_thw=torch.tensor(grids))
+        ref = ref.pooler_output if hasattr(ref, "pooler_output") else ref
+        mine = Q.vit_forward(sd, cfg, px, grids)
+    assert torch.allclose(ref, mine, atol=2e-4, rtol=1e-4), (ref - mine).abs().max()
+
+
+def test_decoder_vs_transformers():
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLTextModel as TM
+    cfg = Q.tiny_cfg(vocab=2048)
+    sd = Q.make_s2_state_dict(cfg, seed=2)
+    _, tc = _hf_cfgs(cfg)
+    m = TM._from_config(tc, attn_implementation="eager").float().eval()
+    tsd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.") and "latent_queries" not in k}
+    m.load_state_dict(tsd, strict=True)
+    rng = np.random.Generator(np.random.PCG64(3))
+    grids = [(1, 8, 12)]
+    ids = torch.tensor([Q.make_prompt(rng, 6, grids, 10, vocab_text=2000) + [5] * 4])
+    # image / vision_start ids exceed the tiny vocabulary: position ids come from the real ids, embeddings are random
+    pos, _ = Q.rope_index(ids, torch.tensor(grids))
+    torch.manual_seed(1)
+    emb = torch.randn(1, ids.shape[1], cfg["hidden"])
+    with torch.no_grad():
+        ref = m(inputs_embeds=emb, position_ids=pos).last_hidden_state
+        mine = Q.text_forward(sd, cfg, emb, pos)
+    assert torch.allclose(ref, mine, atol=3e-4, rtol=1e-4), (ref - mine).abs().max()

@@ -1,0 +1,95 @@
+"""System-2 parity on the GPU: CUDA path (through the C ABI) vs the fp32 oracle (oracle/qwen_oracle.py) on seeded
+weights.  Tolerance: rel-L2 vs the fp32 oracle <= 2e-2 and <= 2x the error of the reference-equivalent
+bf16 PyTorch run; position ids bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _setup(cfg, seed, vocab_rows=None):
+    from internnav_b200.qwen import System2
+    from oracle import qwen_oracle as Q
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = Q.make_s2_state_dict(cfg, seed=seed, vocab_rows=vocab_rows)
+    s2 = System2(cfg, device="cuda:0")
+    s2.load_state_dict(sd)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    return s2, sd_gpu
+
+
+def _check_vit(s2, sd, cfg, grids, seed):
+    from oracle import qwen_oracle as Q
+    n_p = sum(t * h * w for t, h, w in grids)
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(n_p, 1176, generator=g).bfloat16().cuda()
+    out = s2.visual(px, grids)
+    with torch.no_grad():
+        ref = Q.vit_forward(sd, cfg, px.float(), grids)
+        eager = Q.vit_forward({k: v.bfloat16() for k, v in sd.items() if k.startswith("visual.")}, cfg, px, grids)
+    e, ee = _rel(out, ref), _rel(eager, ref)
+    print("vit", grids, "rel err", e, "bf16 eager", ee)
+    assert e < TOL and e < 2 * ee + 2e-3, (e, ee)
+    return out
+
+
+def _check_latents(s2, sd, cfg, prompts, grids_per_prompt, seed):
+    from oracle import qwen_oracle as Q
+    all_grids = [g for gs in grids_per_prompt for g in gs]
+    n_p = sum(t * h * w for t, h, w in all_grids)
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(n_p, 1176, generator=g).bfloat16().cuda()
+    out = s2.generate_latents(prompts, px, all_grids)
+    # position ids of the plan: bit-exact vs the oracle's rope_index
+    plan = s2.llm_plan(prompts, all_grids)
+    pos, delta = s2.positions(plan, len(prompts))
+    off_t, off_p = 0, 0
+    sdb = {k: v.bfloat16() for k, v in sd.items()}
+    for b, (ids, gs) in enumerate(zip(prompts, grids_per_prompt)):
+        npb = sum(t * h * w for t, h, w in gs)
+        ids_t = torch.tensor([ids])
+        full = torch.cat([ids_t, torch.full((1, cfg["n_query"]), Q.TRAJ_TOKEN_INDEX)], dim=1)
+        rp, rd = Q.rope_index(full, torch.tensor(gs).reshape(-1, 3), cfg["v_merge"])
+        L = full.shape[1]
+        assert torch.equal(pos[:, off_t:off_t + L], rp[:, 0]) and int(delta[b]) == int(rd)
+        with torch.no_grad():
+            pxb = px[off_p:off_p + npb]
+            ref = Q.generate_latents(sd, cfg, ids_t, pxb.float(), gs)
+            eager = Q.generate_latents(sdb, cfg, ids_t, pxb, gs)
+        e, ee = _rel(out[b], ref[0]), _rel(eager[0], ref[0])
+        print("latents env", b, "S", L, "rel err", e, "bf16 eager", ee)
+        assert e < TOL and e < 2 * ee + 2e-3, (e, ee)
+        off_t += L
+        off_p += npb
+
+
+def test_tiny_config():
+    from oracle import qwen_oracle as Q
+    cfg = Q.tiny_cfg()
+    s2, sd = _setup(cfg, 1, vocab_rows=512)
+    _check_vit(s2, sd, cfg, [(1, 16, 20), (1, 28, 28)], 0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    gpp = [[(1, 16, 16)], [(1, 8, 12), (1, 28, 28)], [(1, 4, 4)]]
+    prompts = [Q.make_prompt(rng, 7 + 3 * i, gs, 20 - 5 * i) for i, gs in enumerate(gpp)]
+    _check_latents(s2, sd, cfg, prompts, gpp, 1)
+
+
+def test_real_width_shallow():
+    """Qwen2.5-VL-7B widths (1280/16 heads/3420; 3584/28q/4kv/18944) with 2 + 2 layers: every GEMM shape, head layout and
+    padding rule of the full model, at a depth the fp32 oracle finishes in seconds."""
+    from oracle import qwen_oracle as Q
+    cfg = dict(Q.QWEN25VL_7B)
+    cfg.update(v_depth=2, fullatt=[1], layers=2)
+    s2, sd = _setup(cfg, 2, vocab_rows=1024)
+    _check_vit(s2, sd, cfg, [(1, 28, 28)], 3)
+    rng = np.random.Generator(np.random.PCG64(9))
+    gpp = [[(1, 28, 28)], [(1, 28, 28)]]
+    prompts = [Q.make_prompt(rng, 24, gs, 80 - 10 * i) for i, gs in enumerate(gpp)]  # S = 304 / 294
+    _check_latents(s2, sd, cfg, prompts, gpp, 4)
