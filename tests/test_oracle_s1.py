@@ -1,0 +1,131 @@
+"""Pins the System-1 oracle (oracle/navdp_oracle.py) -- CPU only.
+
+tests/golden/s1_reference_outputs.npz and traj_to_actions.json hold OUTPUTS of the reference's own modules
+(/root/reference imported by oracle/gen_golden.py) on seeded weights/inputs that this test regenerates from their seeds.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import navdp_oracle as O, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "s1_reference_outputs.npz"))
+TOL = dict(atol=5e-5, rtol=1e-4)  # fp32 CPU vs fp32 CPU, different summation orders
+
+
+@pytest.fixture(scope="module")
+def sd():
+    torch.set_num_threads(os.cpu_count())
+    return weights.make_state_dict(0)
+
+
+def test_rgbd_encoder_golden(sd):
+    inp = weights.make_inputs(101, B=2)
+    with torch.no_grad():
+        out = O.rgbd_encoder(sd, inp["rgb"], inp["depth"])
+    assert np.allclose(out.numpy(), GOLD["rgbd_B2"], **TOL), np.abs(out.numpy() - GOLD["rgbd_B2"]).max()
+
+
+def test_goal_token_golden(sd):
+    inp = weights.make_inputs(102, B=3)
+    with torch.no_grad():
+        out = O.goal_token(sd, inp["latents"])  # batched call == the reference's per-env bs=1 calls
+    assert np.allclose(out.numpy(), GOLD["goal_B3"], **TOL)
+
+
+@pytest.mark.parametrize("tag,T,k", [("T32", 32, 7), ("T8", 8, 13)])
+def test_predict_noise_golden(sd, tag, T, k):
+    inp = weights.make_inputs(103, B=1, T=T, Ns=32)
+    with torch.no_grad():
+        out = O.predict_noise(sd, inp["x_init"], torch.tensor([k]), inp["goal"], inp["rgbd"])
+    assert np.allclose(out.numpy(), GOLD["eps_" + tag], **TOL), np.abs(out.numpy() - GOLD["eps_" + tag]).max()
+
+
+def test_full_sampling_golden(sd):
+    inp = weights.make_inputs(104, B=1, K=20)
+    with torch.no_grad():
+        out = O.predict_pointgoal_action_async(sd, inp["latents"], inp["rgb"], inp["depth"], inp["x_init"],
+                                               inp["step_noise"], K=20)
+    assert np.allclose(out.numpy(), GOLD["traj_full"], atol=2e-4, rtol=1e-3), np.abs(out.numpy() - GOLD["traj_full"]).max()
+
+
+def test_batched_equals_per_env(sd):
+    """The B-environment generalisation equals the bs=1 reference semantics applied per environment."""
+    inp = weights.make_inputs(106, B=2, T=8, Ns=4)
+    k = torch.tensor([5])
+    with torch.no_grad():
+        both = O.predict_noise(sd, inp["x_init"], k, inp["goal"], inp["rgbd"])
+        for b in range(2):
+            one = O.predict_noise(sd, inp["x_init"][b * 4:(b + 1) * 4], k, inp["goal"][b:b + 1], inp["rgbd"][b:b + 1])
+            assert torch.allclose(both[b * 4:(b + 1) * 4], one, atol=1e-5)
+
+
+def _action_cases():
+    rng = np.random.Generator(np.random.PCG64(105))
+    out = []
+    for i in range(12):
+        out.append(torch.from_numpy(rng.standard_normal((32, 32, 3), dtype=np.float32) * 0.15 +
+                                    np.array([0.5 * np.cos(i), 0.5 * np.sin(i), 0.0], dtype=np.float32)))
+    out.append(torch.from_numpy(GOLD["traj_full"].copy()))
+    return out
+
+
+def test_traj_to_actions_golden_bit_exact():
+    with open(os.path.join(ROOT, "tests", "golden", "traj_to_actions.json")) as fh:
+        gold = json.load(fh)
+    from internnav_b200 import postprocess as P
+    cases = _action_cases()
+    assert len(cases) == len(gold)
+    for tr, g in zip(cases, gold):
+        assert O.traj_to_actions(tr) == g                       # oracle restatement
+        assert P.traj_to_actions(tr.clone()) == g               # product host code
+        assert P.batched_traj_to_actions(tr, 1)[0] == g
+    # empty / degenerate trajectories: the reference returns [] -> action -1 upstream
+    z = torch.zeros(32, 8, 3)
+    assert O.traj_to_actions(z) == [] and P.traj_to_actions(z.clone()) == []
+    # in-place contract of the reference function (vln_utils.py L129)
+    t = cases[0].clone()
+    P.traj_to_actions(t)
+    assert torch.allclose(t[:, :, :2], cases[0][:, :, :2] / 4.0)
+
+
+def test_ddpm_properties():
+    """Known answers of the scheduler restatement: cosine ᾱ endpoints, last step has zero variance and returns the
+    clipped x0 prediction, add_noise/step consistency at t = 0."""
+    from oracle import ddpm
+    s = ddpm.DDPMScheduler(num_train_timesteps=20)
+    import math
+    abar = lambda u: math.cos((u + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+    assert abs(float(s.alphas_cumprod[0]) - abar(1 / 20) / abar(0.0)) < 1e-6
+    assert abs(float(s.alphas_cumprod[9]) - abar(10 / 20) / abar(0.0)) < 1e-5 and float(s.alphas_cumprod[-1]) < 1e-4
+    assert float(s.betas.max()) <= 0.999 + 1e-6
+    s.set_timesteps(20)
+    assert s.timesteps.tolist() == list(range(19, -1, -1))
+    x = torch.randn(4, 8, 3)
+    eps = torch.randn(4, 8, 3)
+    out = s.step(eps, 0, x).prev_sample
+    a0 = s.alphas_cumprod[0]
+    x0 = ((x - (1 - a0) ** 0.5 * eps) / a0 ** 0.5).clamp(-1, 1)
+    assert torch.allclose(out, x0, atol=1e-6)
+
+
+def test_oracle_vs_reference_modules(sd):
+    """Direct comparison with the reference classes (only where /root/reference exists)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    m = ref_loader.build_reference_navdp()
+    m.load_state_dict(sd, strict=True)
+    inp = weights.make_inputs(107, B=1)
+    with torch.no_grad():
+        r = m.rgbd_encoder(inp["rgb"], inp["depth"])
+        o = O.rgbd_encoder(sd, inp["rgb"], inp["depth"])
+        assert torch.allclose(r, o, **TOL)
+        g = O.goal_token(sd, inp["latents"])
+        assert torch.allclose(m.goal_compressor(m.vlm_embed_mlp(inp["latents"]), None), g, **TOL)
+        k = torch.tensor([3])
+        assert torch.allclose(m.predict_noise(inp["x_init"], k, g, r), O.predict_noise(sd, inp["x_init"], k, g, o), **TOL)
