@@ -25,8 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "navdp_denoise": dict(B=8, Ns=32, T=8, K=50,
+    "navdp_denoise": dict(kind="denoise", B=8, Ns=32, T=8, K=50,
                           desc="configs[1]: NavDP denoiser only, 50 denoise steps, 256 trajectories (8 envs x 32) of horizon 8, bf16"),
+    "dual_system": dict(kind="dual", B=64, Ns=32, T=32, K=20, S=304, grid=(1, 28, 28),
+                        desc="configs[3]: full dual-system step (Qwen2.5-VL-7B ViT + LLM prefill -> 4 latents -> NavDP "
+                             "RGB-D encoder + 20-step DDPM, 32 samples, horizon 32 -> action ids), 64 parallel envs, bf16; "
+                             "per env one 392x392 frame (784 patches -> 196 tokens) + 104 text tokens + 4 latent queries = 304"),
 }
 
 
@@ -96,8 +100,181 @@ def denoise_flops_per_sample_step(T, D=384, M=34, Ns=32, layers=16):
     return layers * (28 * T * D * D + 4 * M * D * D / Ns + 4 * T * T * D + 4 * T * M * D)
 
 
+def dual_flops_per_env(wl):
+    """Algorithmic FLOPs of one dual-system policy step: ViT + LLM prefill + RGB-D encoder + denoiser."""
+    S, n_p = wl["S"], wl["grid"][0] * wl["grid"][1] * wl["grid"][2]
+    H, I, L = 3584, 18944, 28
+    llm = L * (2 * S * H * (H + 2 * 512) + 2 * S * H * H + 6 * S * H * I + 4 * S * S * H / 2)
+    Hv, Iv = 1280, 3420
+    vit = 2 * n_p * 1176 * Hv + 32 * (2 * n_p * Hv * 3 * Hv + 2 * n_p * Hv * Hv + 6 * n_p * Hv * Iv) \
+        + 2 * (n_p / 4) * 5120 * (5120 + 3584)
+    D = 384
+    vits = 4 * (12 * (24 * 257 * D * D + 4 * 257 * 257 * D) + 2 * 256 * 588 * D)
+    den = denoise_flops_per_sample_step(wl["T"]) * wl["Ns"] * wl["K"]
+    return dict(llm=llm, vit=vit, rgbd=vits, denoise=den, total=llm + vit + vits + den)
+
+
+def build_dual(dev, wl, rank):
+    """Random-init InternVLA-N1 (Qwen2.5-VL-7B shapes + NavDP) and one step's synthetic inputs."""
+    import numpy as np
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from internnav_b200.manifest import random_navdp_state_dict, random_s2_state_dict
+    from internnav_b200.qwen import QWEN25VL_7B
+    model = InternVLAN1ForCausalLM(QWEN25VL_7B, device=str(dev))
+    model.load_parts(random_s2_state_dict(QWEN25VL_7B, seed=0, device=str(dev)), random_navdp_state_dict(seed=0))
+    torch.cuda.empty_cache()
+    B, S = wl["B"], wl["S"]
+    t, h, w = wl["grid"]
+    n_tok = t * h * w // 4
+    rng = np.random.Generator(np.random.PCG64(77 + rank))
+    n_text = S - 4 - n_tok - 2
+    prompts = []
+    for _ in range(B):
+        pre = rng.integers(0, 151643, 12).tolist()
+        post = rng.integers(0, 151643, n_text - 12).tolist()
+        prompts.append(pre + [151652] + [151655] * n_tok + [151653] + post)
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    host = dict(
+        pixels=torch.randn(B * t * h * w, 1176, generator=g).bfloat16().pin_memory(),
+        rgb=torch.rand(B, 2, 224, 224, 3, generator=g).pin_memory(),
+        depth=(torch.rand(B, 2, 224, 224, 1, generator=g) * 5.0).pin_memory(),
+        x0=torch.randn(B * wl["Ns"], wl["T"], 3, generator=g).pin_memory(),
+        nz=torch.randn(wl["K"] - 1, B * wl["Ns"], wl["T"], 3, generator=g).pin_memory())
+    grids = [list(wl["grid"])] * B
+    return model, prompts, grids, host
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args, wl):
+    if wl["kind"] == "dual":
+        return run_ours_dual(args, wl)
+    return run_ours_denoise(args, wl)
+
+
+def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, extra_cfg, e2e_info, algo_flops_step):
+    import torch.distributed as dist
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    achieved_tf = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
+    peak = pk["tf_sustained"] if ms_per_step > 50 else pk["tf"]
+    cfg = {"workload": args.workload, "description": wl["desc"], "envs_per_gpu": B, "parallelism": "env-sharded x%d" % world,
+           "l2": "flushed (256 MiB memset) between timed steps", "algorithmic_tflop_per_step": algo_flops_step / 1e12,
+           "step_tflops_achieved": algo_flops_step / (ms_per_step * 1e-3) / 1e12}
+    cfg.update(extra_cfg)
+    e2e = {"value": e2e_value, "unit": "policy-steps/s"}
+    e2e.update(e2e_info)
+    out = {
+        "metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": value, "unit": "policy-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "impl": "ours", "config": cfg, "e2e": e2e, "gpu_launches": int(launches["total_launches"]), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "n1::gemm_kernel<BN> (tcgen05, all GEMM launches of one step)",
+                     "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
+                     "traffic": None, "peak_source": pk["src"] + (" sustained" if ms_per_step > 50 else " burst"),
+                     "gemm_launches_per_step": int(prof["gemm_launches"]), "gemm_ms_per_step": prof["gemm_ms"],
+                     "gemm_share_of_step": prof["gemm_ms"] / ms_per_step},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl, budget_s=20.0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _timing_tools(dev, world):
+    import torch.distributed as dist
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, use_events=True):
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            if use_events:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            else:  # includes host work (D2H + numpy tail): wall clock around a synchronised region
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                tot += (time.perf_counter() - t0) * 1e3
+        return tot
+    return barrier, timed
+
+
+def run_ours_dual(args, wl):
+    import torch.distributed as dist
+    from internnav_b200 import _lib
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, prompts, grids, host = build_dual(dev, wl, rank)
+    B = wl["B"]
+    d = {k: v.to(dev) for k, v in host.items()}
+    barrier, timed = _timing_tools(dev, world)
+
+    def step_resident():
+        lat = model.generate_latents(prompts, d["pixels"], grids)
+        return model.generate_traj(lat, d["rgb"], d["depth"], x_init=d["x0"], step_noise=d["nz"])
+
+    def step_e2e():
+        h2d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return model.dual_system_step(prompts, h2d["pixels"], grids, h2d["rgb"], h2d["depth"], x_init=h2d["x0"],
+                                      step_noise=h2d["nz"])[1]
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    _lib.prof_read()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    barrier()
+    launches = _lib.prof_read()
+    launches["total_launches"] //= max(args.steps, 1)
+    clocks = clk.summary()
+    step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps, use_events=False)
+    barrier()
+    _lib.prof_read()
+    _lib.prof_enable(True)
+    step_resident()
+    torch.cuda.synchronize()
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    fl = dual_flops_per_env(wl)
+    _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
+            {"seq_len": wl["S"], "patches_per_env": wl["grid"][1] * wl["grid"][2], "samples_per_env": wl["Ns"],
+             "horizon": wl["T"], "ddpm_steps": wl["K"], "weights": "random-init Qwen2.5-VL-7B shapes + NavDP (bf16)",
+             "tflop_per_env": {k: v / 1e12 for k, v in fl.items()}, "launches_are": "per step"},
+            {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host.values()),
+             "d2h_bytes_per_step": B * wl["Ns"] * wl["T"] * 3 * 4,
+             "api": "InternVLAN1ForCausalLM.dual_system_step (generate_latents + generate_traj + traj_to_actions), pinned host inputs"},
+            fl["total"] * B)
+
+
+def run_ours_denoise(args, wl):
     import torch.distributed as dist
     from internnav_b200 import _lib
     from internnav_b200.manifest import random_navdp_state_dict
@@ -184,48 +361,74 @@ def run_ours(args, wl):
     prof = _lib.prof_read()
     _lib.prof_enable(False)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
-    ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms / 1e3)
-    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-
-    pk = peaks()
-    achieved_tf = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
-    algo_flops_step = denoise_flops_per_sample_step(T) * R * K
-    out = {
-        "metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": value, "unit": "policy-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "impl": "ours",
-        "config": {"workload": args.workload, "description": wl["desc"], "envs_per_gpu": B, "samples_per_env": Ns,
-                   "horizon": T, "ddpm_steps": K, "trajectories_per_s": value * Ns, "parallelism": "env-sharded x%d" % world,
-                   "weights": "random-init NavDP (98.8M params)", "l2": "flushed (256 MiB memset) between timed steps",
-                   "algorithmic_tflop_per_step": algo_flops_step / 1e12,
-                   "step_tflops_achieved": algo_flops_step / (ms_per_step * 1e-3) / 1e12},
-        "e2e": {"value": e2e_value, "unit": "policy-steps/s",
-                "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (h_goal, h_rgbd, h_x0, h_nz)),
-                "d2h_bytes_per_step": R * T * 3 * 4,
-                "api": "NavDP_Policy_DPT_CriticSum_DAT.sample + batched_traj_to_actions, pinned host inputs"},
-        "gpu_launches": int(launches["total_launches"]),
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "n1::gemm_kernel<BN> (tcgen05)", "achieved": achieved_tf,
-                     "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"], "traffic": None,
-                     "peak_source": pk["src"], "gemm_launches_per_step": int(prof["gemm_launches"]),
-                     "gemm_ms_per_step": prof["gemm_ms"], "gemm_share_of_step": prof["gemm_ms"] / ms_per_step},
-    }
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(wl, budget_s=20.0)
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    launches["total_launches"] //= max(args.steps, 1)
+    _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
+            {"samples_per_env": Ns, "horizon": T, "ddpm_steps": K, "weights": "random-init NavDP (98.8M params)",
+             "launches_are": "per step"},
+            {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (h_goal, h_rgbd, h_x0, h_nz)),
+             "d2h_bytes_per_step": R * T * 3 * 4,
+             "api": "NavDP_Policy_DPT_CriticSum_DAT.sample + batched_traj_to_actions, pinned host inputs"},
+            denoise_flops_per_sample_step(T) * R * K)
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
 def cpu_baseline(wl, budget_s=20.0, threads=None):
+    if wl["kind"] == "dual":
+        return cpu_baseline_dual(wl, budget_s, threads)
+    return cpu_baseline_denoise(wl, budget_s, threads)
+
+
+def cpu_baseline_dual(wl, budget_s=20.0, threads=None):
+    """Reference algorithm (oracle ports, fp32 eager PyTorch) on the host cores for ONE environment of the dual-system
+    step, on a bounded sample: the 7B decoder and the 32-block ViT are timed at full width for 2 layers / 2 blocks
+    (the per-layer time is the difference between the 2- and 1-layer runs and is scaled to 28 / 32), the RGB-D encoder
+    runs once in full, the denoiser runs a few of its K steps.  Nothing here is part of the GPU timing."""
+    from oracle import navdp_oracle as O, qwen_oracle as Q, weights
+    import numpy as np
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+
+    def t_of(fn, reps=1):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    grids = [list(wl["grid"])]
+    n_p = wl["grid"][0] * wl["grid"][1] * wl["grid"][2]
+    rng = np.random.Generator(np.random.PCG64(3))
+    with torch.no_grad():
+        times = {}
+        for depth in (1, 2):
+            cfg = dict(Q.QWEN25VL_7B)
+            cfg.update(v_depth=depth, fullatt=[], layers=depth)
+            sd = Q.make_s2_state_dict(cfg, seed=0, vocab_rows=256)
+            px = torch.randn(n_p, 1176)
+            ids = torch.tensor([Q.make_prompt(rng, 12, grids, wl["S"] - 4 - n_p // 4 - 2 - 12)]) % 256
+            ids[ids == 0] = 1
+            emb = torch.randn(1, wl["S"], cfg["hidden"])
+            pos = torch.arange(wl["S"]).view(1, 1, -1).expand(3, 1, -1)
+            times[("vit", depth)] = t_of(lambda: Q.vit_forward(sd, cfg, px, grids))
+            times[("llm", depth)] = t_of(lambda: Q.text_forward(sd, cfg, emb, pos))
+            del sd
+        vit_s = times[("vit", 1)] + 31 * max(times[("vit", 2)] - times[("vit", 1)], 0.0)
+        llm_s = times[("llm", 1)] + 27 * max(times[("llm", 2)] - times[("llm", 1)], 0.0)
+        sd1 = weights.make_state_dict(0)
+        inp = weights.make_inputs(5, B=1, T=wl["T"], Ns=wl["Ns"], K=2)
+        rgbd_s = t_of(lambda: O.rgbd_encoder(sd1, inp["rgb"], inp["depth"]))
+        k = torch.tensor([3])
+        n_den = 3
+        den_s = t_of(lambda: O.predict_noise(sd1, inp["x_init"], k, inp["goal"], inp["rgbd"]), reps=n_den) * wl["K"]
+    total = vit_s + llm_s + rgbd_s + den_s
+    return {"value": 1.0 / total, "unit": "policy-steps/s", "cores": threads, "kind": "port",
+            "seconds_per_env": {"vit": vit_s, "llm": llm_s, "rgbd": rgbd_s, "denoise": den_s},
+            "sample": "1 env, fp32 eager oracle: ViT/LLM timed at 1 and 2 layers of 7B width (S=%d, %d patches) and scaled "
+                      "to 32/28 layers; RGB-D encoder in full; %d of %d denoise steps (32 traj x T=%d) scaled" %
+                      (wl["S"], n_p, n_den, wl["K"], wl["T"])}
+
+
+def cpu_baseline_denoise(wl, budget_s=20.0, threads=None):
     """The reference algorithm (oracle port, fp32 PyTorch eager) on this box's host cores, on a bounded sample of the
     same workload: 1 environment (32 trajectories) for as many denoise steps as fit the budget, scaled linearly to K."""
     from oracle import navdp_oracle as O, weights

@@ -1,0 +1,161 @@
+"""Model-level mirror of the reference InternVLA-N1 dual-system model and its policy wrapper.
+
+`InternVLAN1ForCausalLM` keeps the hot-path API surface of the reference class
+(internnav/model/basemodel/internvla_n1/internvla_n1.py L39-441): `generate_latents(input_ids, pixel_values,
+image_grid_thw)`, `generate_traj(traj_latents, images_dp, depths_dp, ...)`, attributes `.visual`, `.model.navdp`,
+`.config.{system1, n_query}`, `.get_model()`, `.device`.  Both systems execute in libn1b200.so; PyTorch carries the
+tensors.  Everything is batched over B independent environments, each treated exactly like the reference's single one.
+
+Not built yet: the greedy decode loop `generate()`, the NextDiT System-1 branch, and the training
+`forward` -- calling them raises NotImplementedError rather than falling back to anything slower.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .navdp import NavDP_Policy_DPT_CriticSum_DAT
+from .postprocess import batched_traj_to_actions, s1_action_list
+from .qwen import QWEN25VL_7B, System2
+
+TRAJ_TOKEN_INDEX = 151667
+IMAGE_TOKEN_INDEX = 151655
+
+
+class _Model:
+    """Stands in for `InternVLAN1Model` (= `.model` / `.get_model()` of the reference class)."""
+
+    def __init__(self, navdp, s2, config):
+        self.navdp = navdp
+        self._s2 = s2
+        self.config = config
+        self.device = s2.device
+
+    @property
+    def latent_queries(self):
+        raise AttributeError("latent_queries live inside the n1b200 handle; pass them through load_state_dict")
+
+
+class InternVLAN1ForCausalLM:
+    def __init__(self, cfg=None, device="cuda:0", system1="navdp_async", predict_size=32, memory_size=2):
+        if "navdp" not in system1:
+            raise NotImplementedError("n1b200 implements the NavDP System-1 head (system1='navdp_async'); "
+                                      "NextDiT is listed under SURVEY.md §8f")
+        self.cfg = dict(QWEN25VL_7B if cfg is None else cfg)
+        self.device = torch.device(device)
+        self.config = SimpleNamespace(system1=system1, n_query=self.cfg["n_query"], use_cache=True,
+                                      hidden_size=self.cfg["hidden"], image_token_id=IMAGE_TOKEN_INDEX)
+        self._s2 = System2(self.cfg, device=device)
+        navdp = NavDP_Policy_DPT_CriticSum_DAT(memory_size=memory_size, predict_size=predict_size,
+                                               vlm_token_dim=self.cfg["hidden"], navdp_version=0.1, device=device,
+                                               n_query=self.cfg["n_query"])
+        self.model = _Model(navdp, self._s2, self.config)
+
+    # ------------------------------------------------------------------ reference-shaped accessors
+    def get_model(self):
+        return self.model
+
+    def get_n_query(self):
+        return self.config.n_query
+
+    def get_system1_type(self):
+        return self.config.system1
+
+    def eval(self):
+        return self
+
+    def visual(self, pixel_values, grid_thw):
+        grid = grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw
+        return self._s2.visual(pixel_values, grid)
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Full-model state_dict in the reference checkpoint layout: `visual.*`, `model.*` (incl. `model.latent_queries`
+        and `model.navdp.*`).  `lm_head.*` is ignored (generate_latents never uses it)."""
+        navdp_sd = {k[len("model.navdp."):]: v for k, v in state_dict.items() if k.startswith("model.navdp.")}
+        rest = {k: v for k, v in state_dict.items() if not k.startswith("model.navdp.")}
+        self._s2.load_state_dict(rest)
+        if navdp_sd:
+            self.model.navdp.load_state_dict(navdp_sd)
+
+    def load_parts(self, s2_state_dict, navdp_state_dict):
+        self._s2.load_state_dict(s2_state_dict)
+        self.model.navdp.load_state_dict(navdp_state_dict)
+
+    # ------------------------------------------------------------------ hot path
+    @staticmethod
+    def _prompts(input_ids):
+        if torch.is_tensor(input_ids):
+            return [row.tolist() for row in input_ids]
+        return [list(map(int, p)) for p in input_ids]
+
+    def generate_latents(self, input_ids, pixel_values, image_grid_thw):
+        """internvla_n1.py L320-347.  input_ids: [B, S] tensor (equal lengths) or a list of B token-id lists (ragged);
+        pixel_values [sum patches, 1176]; image_grid_thw [n_img, 3] in prompt order -> [B, n_query, hidden]."""
+        grid = image_grid_thw.tolist() if torch.is_tensor(image_grid_thw) else image_grid_thw
+        with torch.no_grad():
+            return self._s2.generate_latents(self._prompts(input_ids), pixel_values, grid)
+
+    def generate_traj(self, traj_latents, images_dp, depths_dp=None, predict_step_nums=32, guidance_scale=1.0,
+                      num_inference_steps=10, num_sample_trajs=32, x_init=None, step_noise=None):
+        """internvla_n1.py L349-441, navdp branch (L434-441): -> [num_sample_trajs * B, predict_size, 3]."""
+        return self.model.navdp.predict_pointgoal_action_async(
+            traj_latents.to(self.device), images_dp, depths_dp, sample_num=num_sample_trajs, x_init=x_init,
+            step_noise=step_noise)
+
+    def dual_system_step(self, input_ids, pixel_values, image_grid_thw, images_dp, depths_dp, x_init=None,
+                         step_noise=None):
+        """One full policy step for B environments: System-2 latent plan -> System-1 trajectories -> action ids.
+        Returns (trajectories [32B, T, 3], list of B action lists (<= 4 non-zero ids each, [] => action -1))."""
+        lat = self.generate_latents(input_ids, pixel_values, image_grid_thw)
+        traj = self.generate_traj(lat, images_dp, depths_dp, x_init=x_init, step_noise=step_noise)
+        acts = [s1_action_list(a) for a in batched_traj_to_actions(traj, lat.shape[0])]
+        return traj, acts
+
+    def generate(self, *a, **k):
+        raise NotImplementedError("greedy decode (model.generate) is not part of the n1b200 hot path yet (SURVEY.md §8f "
+                                  "rank 2); there is no fallback implementation")
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("the training forward (SURVEY.md §8 row a13) is not built yet; no fallback")
+
+    __call__ = forward
+
+
+class S1Output(SimpleNamespace):
+    pass
+
+
+class InternVLAN1Net:
+    """Policy wrapper with the reference's System-1 entry point (internvla_n1_policy.py L200-215)."""
+
+    def __init__(self, model, continuous_traj=True):
+        self.model = model
+        self.continuous_traj = continuous_traj
+
+    def eval(self):
+        return self
+
+    def reset(self):
+        pass
+
+    def s1_step_latent(self, rgb, depth, latent):
+        with torch.no_grad():
+            dp_actions = self.model.generate_traj(traj_latents=latent, images_dp=rgb, depths_dp=depth)
+        B = latent.shape[0]
+        lists = batched_traj_to_actions(dp_actions, B) if self.continuous_traj else None
+        if lists is None:
+            raise NotImplementedError("chunk_token sampling path: use postprocess.chunk_token on a chosen sample")
+        outs = [S1Output(idx=s1_action_list(a)) for a in lists]
+        return outs[0] if B == 1 else outs
+
+
+def preprocess_s1_inputs(rgb_u8, depth_m, goal_rgb_u8, goal_depth_m, depth_clip=5.0):
+    """S1 input preprocessing of the agent (internvla_n1_agent.py L308-334): uint8 RGB -> [0,1], depth metres clipped,
+    stacked as [goal frame, current frame].  Inputs are already 224x224 numpy arrays (resize happens upstream, PIL)."""
+    def f(x):
+        return np.asarray(x, dtype=np.float32) / 255.0
+    d0 = np.minimum(np.asarray(goal_depth_m, dtype=np.float32), depth_clip)
+    d1 = np.minimum(np.asarray(depth_m, dtype=np.float32), depth_clip)
+    rgbs = torch.from_numpy(np.stack([f(goal_rgb_u8), f(rgb_u8)])).unsqueeze(0)
+    depths = torch.from_numpy(np.stack([d0, d1])).unsqueeze(0).unsqueeze(-1)
+    return rgbs, depths

@@ -89,3 +89,56 @@ def random_navdp_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
             t = 0.02 * torch.randn(shape, generator=g)
         out[name] = t.to(device=device, dtype=dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- System 2
+def s2_shapes(cfg):
+    """Qwen2.5-VL parameter names/shapes in the transformers==4.51 checkpoint layout the reference loads, plus
+    InternVLA-N1's `model.latent_queries` (internvla_n1_arch.py L123)."""
+    Hv, H = cfg["v_hidden"], cfg["hidden"]
+    unit = cfg["v_merge"] ** 2
+    out = [("visual.patch_embed.proj.weight", (Hv, 3, cfg["v_tpatch"], cfg["v_patch"], cfg["v_patch"]))]
+    for i in range(cfg["v_depth"]):
+        b = "visual.blocks.%d." % i
+        out += [(b + "norm1.weight", (Hv,)), (b + "norm2.weight", (Hv,)), (b + "attn.qkv.weight", (3 * Hv, Hv)),
+                (b + "attn.qkv.bias", (3 * Hv,)), (b + "attn.proj.weight", (Hv, Hv)), (b + "attn.proj.bias", (Hv,)),
+                (b + "mlp.gate_proj.weight", (cfg["v_inter"], Hv)), (b + "mlp.gate_proj.bias", (cfg["v_inter"],)),
+                (b + "mlp.up_proj.weight", (cfg["v_inter"], Hv)), (b + "mlp.up_proj.bias", (cfg["v_inter"],)),
+                (b + "mlp.down_proj.weight", (Hv, cfg["v_inter"])), (b + "mlp.down_proj.bias", (Hv,))]
+    out += [("visual.merger.ln_q.weight", (Hv,)), ("visual.merger.mlp.0.weight", (Hv * unit, Hv * unit)),
+            ("visual.merger.mlp.0.bias", (Hv * unit,)), ("visual.merger.mlp.2.weight", (cfg["v_out"], Hv * unit)),
+            ("visual.merger.mlp.2.bias", (cfg["v_out"],))]
+    out += [("model.embed_tokens.weight", (cfg["vocab"], H)), ("model.latent_queries", (1, cfg["n_query"], H))]
+    qd, kd = cfg["heads"] * cfg["head_dim"], cfg["kv_heads"] * cfg["head_dim"]
+    for i in range(cfg["layers"]):
+        b = "model.layers.%d." % i
+        out += [(b + "input_layernorm.weight", (H,)), (b + "post_attention_layernorm.weight", (H,)),
+                (b + "self_attn.q_proj.weight", (qd, H)), (b + "self_attn.q_proj.bias", (qd,)),
+                (b + "self_attn.k_proj.weight", (kd, H)), (b + "self_attn.k_proj.bias", (kd,)),
+                (b + "self_attn.v_proj.weight", (kd, H)), (b + "self_attn.v_proj.bias", (kd,)),
+                (b + "self_attn.o_proj.weight", (H, qd)), (b + "mlp.gate_proj.weight", (cfg["inter"], H)),
+                (b + "mlp.up_proj.weight", (cfg["inter"], H)), (b + "mlp.down_proj.weight", (H, cfg["inter"]))]
+    out += [("model.norm.weight", (H,))]
+    return OrderedDict(out)
+
+
+def random_s2_state_dict(cfg, seed=0, device="cuda", dtype=torch.bfloat16):
+    """Random Qwen2.5-VL-shaped weights generated directly on `device` (synthetic benchmark runs; no checkpoints are
+    available offline).  Norm weights ~1, matrices ~N(0, 1/fan_in), embeddings ~N(0, 1)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = OrderedDict()
+    for name, shape in s2_shapes(cfg).items():
+        if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight") \
+                or name.endswith("norm.weight") or name.endswith("ln_q.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g, device=device)
+        elif name in ("model.embed_tokens.weight", "model.latent_queries"):
+            t = torch.randn(shape, generator=g, device=device, dtype=dtype)
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g, device=device, dtype=dtype) / fan_in ** 0.5
+        out[name] = t.to(dtype)
+    return out
