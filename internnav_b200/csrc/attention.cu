@@ -227,6 +227,146 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short-sequence kernel (head_dim 48, <= 8 heads, seq_q <= 32, seq_k <= 64): the NavDP decoder's self / cross attention,
+// the Q-former self-attention and the goal compressor.  One CTA per query sequence, one warp per head.  Q, K, V rows
+// (all heads, contiguous in memory) are staged with fully coalesced 16-byte cp.async; each warp runs QK^T, a
+// single-pass softmax and PV for its head on mma.sync; O is staged back through the Q tile and written coalesced.
+// The generic kernel above spent 4x the work on padding at these shapes (profiles/r1_ncu_small_v0_summary.txt).
+template <int NKP>  // key tiles of 16
+__global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p) {
+  constexpr int HD = 48;
+  extern __shared__ __align__(16) uint8_t ssm[];
+  const int heads = p.heads_q;
+  const int RS = heads * HD * 2 + 16;  // row stride in bytes (+16: conflict-free ldmatrix)
+  const int sq = p.seq_q, sk = p.seq_k;
+  const int sq_pad = (sq + 15) & ~15;
+  constexpr int sk_pad = NKP * 16;
+  uint8_t* sQ = ssm;
+  uint8_t* sK = sQ + sq_pad * RS;
+  uint8_t* sV = sK + sk_pad * RS;
+  const int b = blockIdx.x;
+  const int kb = b / p.kv_div;
+  const bf16* gq = p.q + (long)b * sq * p.ldq;
+  const bf16* gk = p.k + (long)kb * sk * p.ldk;
+  const bf16* gv = p.v + (long)kb * sk * p.ldv;
+  const int chunks = heads * HD / 8;  // 16-byte chunks per row
+  for (int c = threadIdx.x; c < sq_pad * chunks; c += blockDim.x) {
+    const int r = c / chunks, ch = c % chunks;
+    cp_async16(sQ + r * RS + ch * 16, gq + (long)(r < sq ? r : 0) * p.ldq + ch * 8, r < sq);
+  }
+  for (int c = threadIdx.x; c < sk_pad * chunks; c += blockDim.x) {
+    const int r = c / chunks, ch = c % chunks;
+    const bool ok = r < sk;
+    cp_async16(sK + r * RS + ch * 16, gk + (long)(ok ? r : 0) * p.ldk + ch * 8, ok);
+    cp_async16(sV + r * RS + ch * 16, gv + (long)(ok ? r : 0) * p.ldv + ch * 8, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lm = lane >> 3, lr = lane & 7;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int causal_off = sk - sq;
+  if (h < heads) {
+    for (int mt = 0; mt < sq_pad / 16; ++mt) {
+      uint32_t qf[3][4];
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks)
+        ldsm_x4(smem_u32(sQ + (mt * 16 + lr + (lm & 1) * 8) * RS + h * 96 + (ks * 16 + (lm >> 1) * 8) * 2), qf[ks][0],
+                qf[ks][1], qf[ks][2], qf[ks][3]);
+      float s[2 * NKP][4];
+#pragma unroll
+      for (int i = 0; i < 2 * NKP; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int np = 0; np < NKP; ++np) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(smem_u32(sK + (np * 16 + (lm >> 1) * 8 + lr) * RS + h * 96 + (ks * 16 + (lm & 1) * 8) * 2), b0, b1, b2, b3);
+          mma_bf16(s[2 * np], qf[ks], b0, b1);
+          mma_bf16(s[2 * np + 1], qf[ks], b2, b3);
+        }
+      const int row_a = mt * 16 + (lane >> 2), row_b = row_a + 8;
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 2 * NKP; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = i * 8 + (lane & 3) * 2 + (e & 1);
+          const int qi = e < 2 ? row_a : row_b;
+          bool vis = key < sk;
+          if (p.causal) vis = vis && key <= qi + causal_off;
+          s[i][e] = vis ? s[i][e] * sl2 : -INFINITY;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[i][e]);
+        }
+      float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        if (mx[r] == -INFINITY) mx[r] = 0.f;
+      }
+      uint32_t pf[NKP][4];
+#pragma unroll
+      for (int i = 0; i < 2 * NKP; ++i) {
+        const float p0 = exp2f(s[i][0] - mx[0]), p1 = exp2f(s[i][1] - mx[0]);
+        const float p2 = exp2f(s[i][2] - mx[1]), p3 = exp2f(s[i][3] - mx[1]);
+        sum[0] += p0 + p1, sum[1] += p2 + p3;
+        pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+      }
+      float o[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < NKP; ++kk)
+#pragma unroll
+        for (int np = 0; np < 3; ++np) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(sV + (kk * 16 + (lm & 1) * 8 + lr) * RS + h * 96 + (np * 16 + (lm >> 1) * 8) * 2), b0, b1, b2, b3);
+          mma_bf16(o[2 * np], pf[kk], b0, b1);
+          mma_bf16(o[2 * np + 1], pf[kk], b2, b3);
+        }
+      const float inv0 = sum[0] > 0.f ? 1.f / sum[0] : 0.f, inv1 = sum[1] > 0.f ? 1.f / sum[1] : 0.f;
+      // stage O over this warp's own (rows of this m-tile, head columns) slice of the Q tile: nobody else reads it
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        uint8_t* d = sQ + h * 96 + (i * 8 + (lane & 3) * 2) * 2;
+        *reinterpret_cast<uint32_t*>(d + row_a * RS) = pack_bf16(o[i][0] * inv0, o[i][1] * inv0);
+        *reinterpret_cast<uint32_t*>(d + row_b * RS) = pack_bf16(o[i][2] * inv1, o[i][3] * inv1);
+      }
+    }
+  }
+  __syncthreads();
+  bf16* go = p.o + (long)b * sq * p.ldo;
+  for (int c = threadIdx.x; c < sq * chunks; c += blockDim.x) {
+    const int r = c / chunks, ch = c % chunks;
+    *reinterpret_cast<uint4*>(go + (long)r * p.ldo + ch * 8) = *reinterpret_cast<const uint4*>(sQ + r * RS + ch * 16);
+  }
+}
+
+template <int NKP>
+void launch_attn_small(const AttnParams& p, cudaStream_t stream) {
+  const int RS = p.heads_q * 96 + 16;
+  const int smem = (((p.seq_q + 15) & ~15) + 2 * NKP * 16) * RS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn_small_kernel<NKP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 + 2 * NKP * 16) * (8 * 96 + 16));
+    attr_set = true;
+  }
+  attn_small_kernel<NKP><<<p.batch, p.heads_q * 32, smem, stream>>>(p);
+  prof_count_launch();
+  N1_CUDA(cudaGetLastError());
+}
+
 template <int HD>
 void launch_attn(const AttnParams& p, cudaStream_t stream) {
   using C = ACfg<HD>;
@@ -251,6 +391,15 @@ void attention(const AttnParams& p, cudaStream_t stream) {
   N1_CHECK(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "attention: misaligned strides");
   N1_CHECK(!p.cu_q || p.max_seq_q > 0, "attention: varlen needs max_seq_q");
   N1_CHECK(p.batch <= 65535 && p.heads_q <= 65535, "attention: grid too large");
+  if (p.hd == 48 && !p.cu_q && !p.cu_k && p.heads_q == p.heads_kv && p.heads_q <= 8 && p.seq_q <= 32 && p.seq_k <= 64 &&
+      p.ldo % 8 == 0) {
+    const int nkp = (p.seq_k + 15) / 16;
+    if (nkp == 1) launch_attn_small<1>(p, stream);
+    else if (nkp == 2) launch_attn_small<2>(p, stream);
+    else if (nkp == 3) launch_attn_small<3>(p, stream);
+    else launch_attn_small<4>(p, stream);
+    return;
+  }
   switch (p.hd) {
     case 48: launch_attn<48>(p, stream); break;
     case 64: launch_attn<64>(p, stream); break;

@@ -9,6 +9,8 @@
 // This one kernel carries every Linear / Conv-as-GEMM on the InternVLA-N1 hot path:
 // the reference reaches cuBLAS through nn.Linear at navdp.py L57-66/L94-100, navdp_backbone.py L147-149,
 // dinov2_layers/{attention.py L46-48, mlp.py L30-32, patch_embed.py L65} and the Qwen2.5-VL blocks.
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -64,10 +66,17 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
   tn = r / gsize;
 }
 
-template <int BN>
+// CM = cluster size along M.  With CM > 1 the CM CTAs of a cluster work on CM vertically adjacent tiles of the same
+// N panel: every CTA fetches 1/CM of the W tile and multicasts it to its peers, which divides the L2 -> SMEM traffic
+// for W by CM (the short-K GEMMs of the path are L2-bandwidth-bound, profiles/r1_ncu_small_v0_summary.txt).
+template <int BN, int CM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using C = Cfg<BN>;
+  constexpr uint16_t kMask = (1u << CM) - 1;
+  const int rank = CM > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
+  const int super_m = (args.tiles_m + CM - 1) / CM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -81,7 +90,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = args.tiles_m * args.tiles_n;
+  const int num_tiles = super_m * args.tiles_n;  // cluster-level (super) tiles: CM m-tiles x 1 n-tile
   const int nkb = (args.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -89,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CM);  // every CTA of the cluster releases the slot (its W slice lives in all of them)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -102,7 +111,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CM > 1)
+    cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive reaches them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -111,14 +123,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int tm, tn;
-        decode_tile(tile, args.tiles_m, args.tiles_n, tm, tn);
+        decode_tile(tile, super_m, args.tiles_n, tm, tn);
+        tm = tm * CM + rank;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
           tma_load_2d(sA + stage * C::kABytes, &tmA, &full[stage], kb * BK, tm * BM);
-          tma_load_2d(sB + stage * C::kBBytes, &tmB, &full[stage], kb * BK, tn * BN);
+          if (CM == 1) {
+            tma_load_2d(sB + stage * C::kBBytes, &tmB, &full[stage], kb * BK, tn * BN);
+          } else {
+            constexpr int kSliceRows = BN / CM;
+            tma_load_2d_mc(sB + stage * C::kBBytes + rank * kSliceRows * BK * 2, &tmB, &full[stage], kb * BK,
+                           tn * BN + rank * kSliceRows, kMask);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -126,6 +145,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
@@ -134,7 +154,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -148,7 +168,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (CM == 1)
+            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          else
+            umma_commit_mc(&empty[stage], kMask);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -169,9 +192,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = args.act == ACT_SWIGLU;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int tm, tn;
-      decode_tile(tile, args.tiles_m, args.tiles_n, tm, tn);
+      decode_tile(tile, super_m, args.tiles_n, tm, tn);
+      tm = tm * CM + rank;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = tm * BM + quarter * 32 + lane;
@@ -294,7 +318,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CM > 1)
+    cluster_sync_all();  // no CTA may retire while a peer can still multicast into it or arrive on its barriers
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
@@ -335,22 +362,47 @@ CUtensorMap make_map(const bf16* ptr, long rows, long cols, long ld, int box_row
   return m;
 }
 
-template <int BN>
+template <int BN, int CM>
 void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   static std::once_flag once;
+  static int max_clusters = 0;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaFuncSetAttribute(gemm_kernel<BN, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    max_clusters = device_sm_count() / CM;
+    if (CM > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(device_sm_count() / CM * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+      cfg.attrs = &at, cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, CM>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    }
   });
   a.tiles_m = (M + BM - 1) / BM;
   a.tiles_n = (N + BN - 1) / BN;
   CUtensorMap tmA = make_map(A, M, K, lda, BM);
-  CUtensorMap tmB = make_map(W, N, K, ldw, BN);
-  const int tiles = a.tiles_m * a.tiles_n;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  CUtensorMap tmB = make_map(W, N, K, ldw, BN / CM);
+  const int super_tiles = ((a.tiles_m + CM - 1) / CM) * a.tiles_n;
+  const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
+  if (CM == 1) {
+    gemm_kernel<BN, CM><<<clusters, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cfg.attrs = &at, cfg.numAttrs = 1;
+    N1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CM>, tmA, tmB, a));
+  }
   N1_CUDA(cudaGetLastError());
 }
+
+std::atomic<int> g_cluster_m{2};  // developer knob (N1_GEMM_CLUSTER=1 disables the multicast path)
 
 // ---- profiling state
 std::atomic<long> g_total_launches{0}, g_gemm_launches{0};
@@ -385,6 +437,7 @@ ProfStats prof_read_and_reset() {
 int device_sm_count() {
   static int sms = 0;
   if (!sms) {
+    if (const char* e = getenv("N1_GEMM_CLUSTER")) g_cluster_m = atoi(e);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -428,12 +481,18 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
   long best = cost(256);
   if (cost(128) < best) best = cost(128), bn = 128;
   if (cost(64) < best) bn = 64;
-  if (bn == 256)
-    launch<256>(A, lda, W, ldw, M, N, K, a, stream);
-  else if (bn == 128)
-    launch<128>(A, lda, W, ldw, M, N, K, a, stream);
-  else
-    launch<64>(A, lda, W, ldw, M, N, K, a, stream);
+  // clusters of 2 along M (W multicast) whenever there are at least two M tiles to pair up
+  const bool pair = tm >= 2 && g_cluster_m.load() >= 2;
+  if (bn == 256) {
+    if (pair) launch<256, 2>(A, lda, W, ldw, M, N, K, a, stream);
+    else launch<256, 1>(A, lda, W, ldw, M, N, K, a, stream);
+  } else if (bn == 128) {
+    if (pair) launch<128, 2>(A, lda, W, ldw, M, N, K, a, stream);
+    else launch<128, 1>(A, lda, W, ldw, M, N, K, a, stream);
+  } else {
+    if (pair) launch<64, 2>(A, lda, W, ldw, M, N, K, a, stream);
+    else launch<64, 1>(A, lda, W, ldw, M, N, K, a, stream);
+  }
   if (prof) {
     cudaEventRecord(ev.b, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);
