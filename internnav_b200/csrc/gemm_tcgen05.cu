@@ -35,7 +35,8 @@ struct Cfg {
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+  static constexpr int kStoreBytes = kEpiWarps * 2 * 2048;  // per-warp double-buffered 32x32 bf16 staging for TMA stores
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStoreBytes + 1024;  // +1024: manual alignment
 };
 
 struct GemmArgs {
@@ -51,6 +52,7 @@ struct GemmArgs {
   int out_fp32;
   int rows_per_group, group_stride, group_offset;
   const float* row_add;
+  int tma_store;  // bf16 output tile goes registers -> smem staging -> cp.async.bulk.tensor store (full-sector writes)
 };
 
 // Grouped rasterisation: consecutive tile ids walk 8 M-tiles before moving to the next N-tile, so the CTAs
@@ -71,7 +73,8 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
 // for W by CM (the short-K GEMMs of the path are L2-bandwidth-bound, profiles/r1_ncu_small_v0_summary.txt).
 template <int BN, int CM>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
   using C = Cfg<BN>;
   constexpr uint16_t kMask = (1u << CM) - 1;
   const int rank = CM > 1 ? (int)cluster_ctarank() : 0;
@@ -87,6 +90,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * C::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* sStore = smem + C::kStages * C::kStageBytes + C::kBarBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +100,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (args.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CM);  // every CTA of the cluster releases the slot (its W slice lives in all of them)
@@ -192,6 +197,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = args.act == ACT_SWIGLU;
+    uint8_t* my_store = sStore + (warp - 2) * 4096;
+    int sbuf = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int tm, tn;
       decode_tile(tile, super_m, args.tiles_n, tm, tn);
@@ -225,6 +232,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
             }
           }
+        }
+        if (swiglu && args.tma_store) {
+          // (gate, up) interleaved: 32 accumulator columns -> 16 outputs, staged as a 32 x 16 tile
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = my_store + sbuf * 2048;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 pk;
+            pk.x = pack_bf16(silu(v[2 * j + 0]) * v[2 * j + 1], silu(v[2 * j + 2]) * v[2 * j + 3]);
+            pk.y = pack_bf16(silu(v[2 * j + 4]) * v[2 * j + 5], silu(v[2 * j + 6]) * v[2 * j + 7]);
+            pk.z = pack_bf16(silu(v[2 * j + 8]) * v[2 * j + 9], silu(v[2 * j + 10]) * v[2 * j + 11]);
+            pk.w = pack_bf16(silu(v[2 * j + 12]) * v[2 * j + 13], silu(v[2 * j + 14]) * v[2 * j + 15]);
+            *reinterpret_cast<uint4*>(sb + lane * 32 + j * 2) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sb, col0 >> 1, tm * BM + quarter * 32);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+          continue;
         }
         if (swiglu) {
           // (gate, up) interleaved: 32 accumulator columns -> 16 outputs
@@ -285,6 +315,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        }  // row_ok (loads)
+        if (args.tma_store) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = my_store + sbuf * 2048;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pk.x = pack_bf16(v[j + 0], v[j + 1]);
+            pk.y = pack_bf16(v[j + 2], v[j + 3]);
+            pk.z = pack_bf16(v[j + 4], v[j + 5]);
+            pk.w = pack_bf16(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(sb + lane * 64 + j * 2) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sb, col0, tm * BM + quarter * 32);  // rows >= M / cols >= N are clipped by the tensor map
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+          continue;
+        }
+        if (row_ok) {
         if (args.out_fp32) {
           float* orow = reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0;
 #pragma unroll
@@ -315,6 +369,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         acc_phase ^= 1;
       }
     }
+    if (args.tma_store && lane == 0) tma_store_wait<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -346,17 +402,18 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = [box_rows, 64].
-CUtensorMap make_map(const bf16* ptr, long rows, long cols, long ld, int box_rows) {
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = [box_rows, box_cols];
+// operands use box_cols = 64 with the 128-byte swizzle, output staging tiles are unswizzled.
+CUtensorMap make_map(const bf16* ptr, long rows, long cols, long ld, int box_rows, int box_cols = BK, bool swizzle = true) {
   N1_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand not 16-byte aligned");
   N1_CHECK(ld % 8 == 0, "GEMM operand leading dimension must be a multiple of 8 elements");
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(-5, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return m;
@@ -385,10 +442,15 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   a.tiles_n = (N + BN - 1) / BN;
   CUtensorMap tmA = make_map(A, M, K, lda, BM);
   CUtensorMap tmB = make_map(W, N, K, ldw, BN / CM);
+  CUtensorMap tmC = tmA;  // placeholder when the direct-store epilogue is used
+  if (a.tma_store) {
+    const bool sw = a.act == ACT_SWIGLU;
+    tmC = make_map(static_cast<const bf16*>(a.out), M, sw ? N / 2 : N, a.ldo, 32, sw ? 16 : 32, false);
+  }
   const int super_tiles = ((a.tiles_m + CM - 1) / CM) * a.tiles_n;
   const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
   if (CM == 1) {
-    gemm_kernel<BN, CM><<<clusters, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+    gemm_kernel<BN, CM><<<clusters, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, a);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes;
@@ -397,12 +459,13 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
     cfg.attrs = &at, cfg.numAttrs = 1;
-    N1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CM>, tmA, tmB, a));
+    N1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CM>, tmA, tmB, tmC, a));
   }
   N1_CUDA(cudaGetLastError());
 }
 
-std::atomic<int> g_cluster_m{2};  // developer knob (N1_GEMM_CLUSTER=1 disables the multicast path)
+std::atomic<int> g_cluster_m{2};
+std::atomic<int> g_tma_store{1};  // developer knob (N1_GEMM_TMA_STORE=0 selects the direct-store epilogue)  // developer knob (N1_GEMM_CLUSTER=1 disables the multicast path)
 
 // ---- profiling state
 std::atomic<long> g_total_launches{0}, g_gemm_launches{0};
@@ -438,6 +501,7 @@ int device_sm_count() {
   static int sms = 0;
   if (!sms) {
     if (const char* e = getenv("N1_GEMM_CLUSTER")) g_cluster_m = atoi(e);
+    if (const char* e = getenv("N1_GEMM_TMA_STORE")) g_tma_store = atoi(e);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -459,6 +523,10 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
   a.act = e.act, a.out_fp32 = e.out_fp32;
   a.rows_per_group = e.rows_per_group, a.group_stride = e.group_stride, a.group_offset = e.group_offset;
   a.row_add = e.row_add;
+  a.tma_store = (!e.out_fp32 && e.rows_per_group == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % 8 == 0 &&
+                 g_tma_store.load() != 0)
+                    ? 1
+                    : 0;
   // Tile-width choice: fewest waves first, then the widest tile (fewer A re-reads, longer MMA bursts).
   const int sms = device_sm_count();
   const int tm = (M + BM - 1) / BM;
