@@ -232,19 +232,22 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// Exact-GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. far below
-// bf16 output rounding) -- ~15 instructions instead of erff's ~40; the GELU epilogue was issue-bound with erff
-// (profiles/r1_ncu_small_v0_summary.txt).
+// Exact-GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.28,
+//   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |abs err| <= 3e-7 (far below bf16 output rounding):
+// one MUFU (rcp) + ~14 FMA/MUL instead of erff's ~40 instructions.  The GELU epilogue of the short-K FF GEMMs was
+// issue-bound with erff (profiles/r1_ncu_small_v0_summary.txt).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x| / sqrt 2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  float d = fmaf(0.0000430638f, z, 0.0002765672f);
+  d = fmaf(d, z, 0.0001520143f);
+  d = fmaf(d, z, 0.0092705272f);
+  d = fmaf(d, z, 0.0422820123f);
+  d = fmaf(d, z, 0.0705230784f);
+  d = fmaf(d, z, 1.0f);
+  float r = __fdividef(1.0f, d);
+  r *= r, r *= r, r *= r, r *= r;  // ^16
+  return 0.5f * x * (1.0f + copysignf(1.0f - r, x));
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace n1

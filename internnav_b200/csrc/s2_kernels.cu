@@ -47,18 +47,29 @@ __global__ void mrope_table_kernel(const int* __restrict__ pos3, float2* __restr
   cs[i] = make_float2(cn, sn);
 }
 
+// 8 rotation pairs (two 16-byte vectors) per thread; half % 8 == 0.
 __global__ void apply_rope_kernel(bf16* __restrict__ x, int ld, const float2* __restrict__ cs, long tokens, int heads,
                                   int half) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long per_tok = (long)heads * half;
+  const int vec = half / 8;
+  const long per_tok = (long)heads * vec;
   if (i >= tokens * per_tok) return;
   const long t = i / per_tok;
-  const int h = (i % per_tok) / half, j = i % half;
+  const int h = (i % per_tok) / vec, j = (i % vec) * 8;
   bf16* p = x + t * ld + (long)h * 2 * half + j;
-  const float2 c = cs[t * half + j];
-  const float a = __bfloat162float(p[0]), b = __bfloat162float(p[half]);
-  p[0] = __float2bfloat16(a * c.x - b * c.y);
-  p[half] = __float2bfloat16(b * c.x + a * c.y);
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + half);
+  const float4* c4 = reinterpret_cast<const float4*>(cs + t * half + j);  // (cos, sin) pairs
+  uint32_t* au = reinterpret_cast<uint32_t*>(&a);
+  uint32_t* bu = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 c = __ldg(c4 + k);  // c.x,c.y = cos,sin of pair 2k ; c.z,c.w of pair 2k+1
+    const float a0 = bf16_lo(au[k]), a1 = bf16_hi(au[k]), b0 = bf16_lo(bu[k]), b1 = bf16_hi(bu[k]);
+    au[k] = pack_bf16(a0 * c.x - b0 * c.y, a1 * c.z - b1 * c.w);
+    bu[k] = pack_bf16(b0 * c.x + a0 * c.y, b1 * c.z + a1 * c.w);
+  }
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + half) = b;
 }
 
 __global__ void build_embeds_kernel(const int* __restrict__ kind, const int* __restrict__ src,
@@ -95,7 +106,8 @@ void mrope_table(const int* pos3, float2* cs, long tokens, int half, int sec_t, 
   N1_CUDA(cudaGetLastError());
 }
 void apply_rope(bf16* x, int ld, const float2* cs, long tokens, int heads, int hd, cudaStream_t s) {
-  apply_rope_kernel<<<nblk(tokens * heads * (hd / 2)), 256, 0, s>>>(x, ld, cs, tokens, heads, hd / 2);
+  N1_CHECK((hd / 2) % 8 == 0 && ld % 8 == 0, "apply_rope: head_dim / 2 and ld must be multiples of 8");
+  apply_rope_kernel<<<nblk(tokens * heads * (hd / 16)), 256, 0, s>>>(x, ld, cs, tokens, heads, hd / 2);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
