@@ -169,6 +169,11 @@ int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, in
 int n1_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, void* out, int ldo, int M, int N, int K,
                const float* bias, const float* gamma, const void* residual_bf16, int ldr, int act, int out_fp32,
                void* stream);
+/* NavDP decoder FF block in one kernel: out = residual + W2 GELU(W1 x + b1) + b2; x [M,384], W1 [1536,384], W2 [384,1536]
+ * (replaces linear1 / gelu / linear2 / residual of nn.TransformerDecoderLayer, navdp.py L57-66).  cluster: 1 or 2. */
+int n1_op_fused_mlp(const void* x_bf16, int ldx, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                    const float* b2, const void* residual_bf16, int ldr, void* out_bf16, int ldo, int M, int cluster,
+                    void* stream);
 int n1_op_layernorm(const void* x_bf16, int ldx, void* y_bf16, int ldy, const float* w, const float* b, int rows, int D,
                     float eps, int rms, void* stream);
 /* q/k/v/o bf16 with row strides ld*; sequences fixed-length (cu_* NULL) or varlen (int32 prefix sums on device) */

@@ -57,6 +57,8 @@ SYMBOLS = {
                              ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_void_p]),
+    "n1_op_fused_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                c_int, c_int, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
                                 c_void_p]),
     "n1_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -158,3 +160,16 @@ def attention(q, k, v, heads_q, heads_kv, head_dim, batch, seq_q, seq_k, cu_q=No
                                 seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div, 1 if causal else 0,
                                 float(scale), stream_ptr()))
     return o
+
+
+def fused_mlp(x, w1, b1, w2, b2, residual=None, out=None, cluster=2):
+    """out = residual + gelu(x @ w1.T + b1) @ w2.T + b2 for the NavDP decoder widths (384 -> 1536 -> 384)."""
+    assert x.dtype == torch.bfloat16 and x.shape[1] == 384 and w1.shape == (1536, 384) and w2.shape == (384, 1536)
+    assert w1.is_contiguous() and w2.is_contiguous() and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape[0], 384, device=x.device, dtype=torch.bfloat16)
+    check(lib().n1_op_fused_mlp(c_void_p(x.data_ptr()), x.stride(0), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                c_void_p(residual.data_ptr()) if residual is not None else None,
+                                residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
+                                out.stride(0), x.shape[0], cluster, stream_ptr()))
+    return out

@@ -327,6 +327,13 @@ int n1_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ld
   });
 }
 
+int n1_op_fused_mlp(const void* x, int ldx, const void* w1, const float* b1, const void* w2, const float* b2,
+                    const void* residual, int ldr, void* out, int ldo, int M, int cluster, void* stream) {
+  return guard([&] {
+    fused_mlp_384(B16(x), ldx, B16(w1), b1, B16(w2), b2, B16(residual), ldr, B16(out), ldo, M, cluster, S(stream));
+  });
+}
+
 int n1_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* w, const float* b, int rows, int D, float eps,
                     int rms, void* stream) {
   return guard([&] { layernorm(B16(x), ldx, B16(y), ldy, w, b, rows, D, eps, rms, S(stream)); });

@@ -54,6 +54,10 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
 
 int device_sm_count();
 
+// Fused MLP of the NavDP decoder (fused_mlp.cu): out = residual + W2 GELU(W1 x + b1) + b2, D = 384, F = 1536.
+void fused_mlp_384(const bf16* x, int ldx, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
+                   const bf16* residual, int ldr, bf16* out, int ldo, int M, int cluster, cudaStream_t stream);
+
 // Launch accounting (always on) and optional per-GEMM event timing (bench.py's roofline pass).
 struct ProfStats {
   double gemm_ms = 0, gemm_flops = 0;

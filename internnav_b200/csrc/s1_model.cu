@@ -2,6 +2,7 @@
 #include "s1_model.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -29,6 +30,16 @@ LNp load_ln(Arena& a, const WeightSource& ws, const std::string& prefix, cudaStr
 void linear(const Lin& L, const bf16* A, int lda, void* out, int ldo, int M, GemmEpilogue e, cudaStream_t s) {
   e.bias = L.b;
   gemm_bf16(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, s);
+}
+
+// N1_FUSED_MLP: 0 = two GEMMs, 1 = fused kernel, 2 (default) = fused kernel with 2-CTA weight multicast
+int fused_mlp_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("N1_FUSED_MLP");
+    mode = e ? atoi(e) : 2;
+  }
+  return mode;
 }
 
 // torch.nn.functional.interpolate(mode="bicubic", scale_factor=s, antialias=False, align_corners=False) restated
@@ -428,10 +439,15 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     linear(L.ca_out, d.att, D, d.x, D, (int)R, res, s);
 
     layernorm(d.x, D, d.ln, D, L.n3.w, L.n3.b, (int)R, D, 1e-5f, 0, s);
-    GemmEpilogue gelu;
-    gelu.act = ACT_GELU;
-    linear(L.ff1, d.ln, D, d.hid, 4 * D, (int)R, gelu, s);
-    linear(L.ff2, d.hid, 4 * D, d.x, D, (int)R, res, s);
+    if (fused_mlp_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536) {
+      // FF block in one kernel: the [R, 1536] hidden never leaves the SM (fused_mlp.cu)
+      fused_mlp_384(d.ln, D, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, d.x, D, d.x, D, (int)R, fused_mlp_mode(), s);
+    } else {
+      GemmEpilogue gelu;
+      gelu.act = ACT_GELU;
+      linear(L.ff1, d.ln, D, d.hid, 4 * D, (int)R, gelu, s);
+      linear(L.ff2, d.hid, 4 * D, d.x, D, (int)R, res, s);
+    }
   }
   head_ddpm(d.x, final_ln_.w, final_ln_.b, head_w_, head_b_, R, mode, x_io, noise, eps, cf, s);
 }

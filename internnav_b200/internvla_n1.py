@@ -111,12 +111,32 @@ class InternVLAN1ForCausalLM:
         acts = [s1_action_list(a) for a in batched_traj_to_actions(traj, lat.shape[0])]
         return traj, acts
 
+    def s1_training_loss(self, traj_hidden_states, traj_images, traj_depths, traj_poses, video_frame_num, noise=None,
+                         timesteps=None):
+        """The navdp_async branch of the training forward, from the gathered latent states on (internvla_n1.py
+        L231-303): traj_hidden_states [B, n_query, H] (the 4 states at t_s_pos); traj_images [B, f, 224, 224, 3];
+        traj_depths [B, f, 224, 224]; traj_poses [B, f, 32, 3]; video_frame_num [B] -> scalar loss (forward only)."""
+        B, f = traj_images.shape[:2]
+        hs = traj_hidden_states.unsqueeze(1).repeat(1, f, 1, 1).flatten(0, 1)
+        loss_mask = torch.arange(f, device=traj_images.device).expand(B, f) < video_frame_num.to(traj_images.device).unsqueeze(1)
+        cur_images, cur_depths = traj_images.flatten(0, 1), traj_depths.flatten(0, 1)
+        goal_images = traj_images[:, 0:1].repeat(1, f, 1, 1, 1).flatten(0, 1)
+        goal_depths = traj_depths[:, 0:1].repeat(1, f, 1, 1).flatten(0, 1)
+        images_dp = torch.stack([goal_images, cur_images], dim=1)
+        depths_dp = torch.stack([goal_depths, cur_depths], dim=1).unsqueeze(-1)
+        pred, eps = self.model.navdp.forward_vlm_traj(hs, images_dp, depths_dp, traj_poses, noise=noise,
+                                                      timesteps=timesteps)
+        err = (pred.float() - eps.float()).square()
+        mask = loss_mask.flatten(0, 1)[:, None, None].to(err.device)
+        return (err * mask).sum() / mask.sum() / (err.shape[1] * err.shape[2])
+
     def generate(self, *a, **k):
         raise NotImplementedError("greedy decode (model.generate) is not part of the n1b200 hot path yet (SURVEY.md §8f "
                                   "rank 2); there is no fallback implementation")
 
     def forward(self, *a, **k):
-        raise NotImplementedError("the training forward (SURVEY.md §8 row a13) is not built yet; no fallback")
+        raise NotImplementedError("the full training forward/backward (SURVEY.md §8 row a13) is not built: the System-1 "
+                                  "loss is available forward-only as s1_training_loss(); no fallback")
 
     __call__ = forward
 

@@ -198,6 +198,36 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
                                  for _ in range(K - 1)]) if K > 1 else None
         return x_init, noise
 
+    # ------------------------------------------------------------------ training-branch forward (no autograd yet)
+    def add_noise(self, original_samples, noise, timesteps):
+        """DDPMScheduler.add_noise (navdp.py L173): sqrt(acp_t) x0 + sqrt(1 - acp_t) eps, tables from the library."""
+        K = self.num_train_timesteps
+        buf = (ctypes.c_float * (K * 5))()
+        check(_lib.lib().n1_ddpm_tables(K, buf))
+        tab = torch.tensor(list(buf), dtype=torch.float32, device=original_samples.device).view(K, 5)
+        t = timesteps.to(original_samples.device).long()
+        s2 = tab[t, 0].view(-1, 1, 1)                 # sqrt(1 - acp_t)
+        s1 = (1.0 / tab[t, 1]).view(-1, 1, 1)         # sqrt(acp_t)
+        return (s1 * original_samples.float() + s2 * noise.float()).to(original_samples.dtype)
+
+    def forward_vlm_traj(self, vlm_tokens, input_images, input_depths, tensor_label_actions,
+                         tensor_augment_actions=None, noise=None, timesteps=None):
+        """navdp.py L291-312 (the System-1 half of the training forward): one noise prediction per
+        (episode, frame) sample with its own timestep and its own condition.  FORWARD ONLY -- the returned tensors
+        carry no autograd graph (the backward kernels are not built); `noise` / `timesteps` may be passed in, else
+        they are drawn like `sample_noise` (navdp.py L165-175).  Returns (noise_pred, noise)."""
+        label = tensor_label_actions.flatten(0, 1).to(self._device)
+        n = label.shape[0]
+        if noise is None:
+            noise = torch.randn(label.shape, dtype=label.dtype).to(self._device)
+        if timesteps is None:
+            timesteps = torch.randint(0, self.num_train_timesteps, (n,)).long()
+        noisy = self.add_noise(label, noise.to(self._device), timesteps)
+        goal = self.goal_embed(vlm_tokens)
+        rgbd = self.rgbd_encoder(input_images, input_depths)
+        pred = self.predict_noise(noisy.float(), timesteps, goal, rgbd)
+        return pred.to(label.dtype), noise.to(self._device)
+
     def predict_pointgoal_action_async(self, vlm_tokens, input_images=None, input_depths=None, vlm_mask=None,
                                        sample_num=32, x_init=None, step_noise=None):
         """navdp.py L197-253.  Reference semantics are bs = 1 (extra rows are dropped at L227-231); here every one of

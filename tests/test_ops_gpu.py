@@ -195,3 +195,21 @@ def test_attention_varlen(L):
                             v[sl].float().view(1, n, H, hd).transpose(1, 2), causal, hd ** -0.5)
             assert _rel(o[sl], ref.transpose(1, 2).reshape(n, H * hd)) < 8e-3
             s += n
+
+
+@pytest.mark.parametrize("M,cluster", [(128, 1), (1000, 1), (256, 2), (1000, 2), (65536 // 8, 2), (300, 2)])
+def test_fused_mlp(L, M, cluster):
+    torch.manual_seed(M)
+    x = torch.randn(M, 384, device="cuda").bfloat16()
+    w1 = (torch.randn(1536, 384, device="cuda") / math.sqrt(384)).bfloat16()
+    w2 = (torch.randn(384, 1536, device="cuda") / math.sqrt(1536)).bfloat16()
+    b1, b2 = torch.randn(1536, device="cuda") * 0.1, torch.randn(384, device="cuda") * 0.1
+    res = torch.randn(M, 384, device="cuda").bfloat16()
+    ref = res.float() + torch.nn.functional.gelu(x.float() @ w1.float().T + b1) @ w2.float().T + b2
+    out = L.fused_mlp(x, w1, b1, w2, b2, residual=res, cluster=cluster)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 8e-3, _rel(out, ref)
+    # in place on the residual stream, as the decoder uses it
+    r2 = res.clone()
+    L.fused_mlp(x, w1, b1, w2, b2, residual=r2, out=r2, cluster=cluster)
+    assert _rel(r2, ref) < 8e-3

@@ -121,3 +121,27 @@ def test_full_s1_config2_shape(env):
     e = _rel(out[:64], ref)
     print("cfg2 traj rel err", e)
     assert e < 4e-2
+
+
+def test_training_branch_forward_loss(env):
+    """SURVEY §8 row a13, System-1 half, forward only: masked-MSE loss of the navdp_async branch vs the oracle."""
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from oracle import navdp_oracle as O
+    m, sd, sdb = env
+    g = torch.Generator().manual_seed(5)
+    B, f = 2, 3
+    hs = torch.randn(B, 4, 3584, generator=g).bfloat16().cuda()
+    imgs = torch.rand(B, f, 224, 224, 3, generator=g).cuda()
+    deps = (torch.rand(B, f, 224, 224, generator=g) * 5).cuda()
+    poses = (torch.randn(B, f, 32, 3, generator=g) * 0.5).cuda()
+    vfn = torch.tensor([3, 2]).cuda()
+    noise = torch.randn(B * f, 32, 3, generator=g).cuda()
+    ts = torch.randint(0, 20, (B * f,), generator=g)
+    model = InternVLAN1ForCausalLM.__new__(InternVLAN1ForCausalLM)
+    from types import SimpleNamespace
+    model.model = SimpleNamespace(navdp=m)
+    loss = model.s1_training_loss(hs, imgs, deps, poses, vfn, noise=noise, timesteps=ts)
+    with torch.no_grad():
+        ref = O.s1_training_loss(sd, hs.float(), imgs, deps, poses, vfn, noise, ts.cuda())
+    print("s1 loss", float(loss), "oracle", float(ref))
+    assert abs(float(loss) - float(ref)) / float(ref) < 2e-2
