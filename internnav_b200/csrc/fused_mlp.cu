@@ -21,6 +21,7 @@ namespace {
 constexpr int D = 384, F = 1536, BM = 128, HC = 64;  // hidden chunk width
 constexpr int NCH = F / HC;                          // 24 chunks
 constexpr int kSlots = 4, kSlotBytes = 24576;
+constexpr int kLag = 2;                              // GEMM2(j) is issued after GEMM1(j + kLag)
 constexpr int kABytes = BM * D * 2;                  // 98304: 6 k-blocks of [128 x 64]
 constexpr int kHBytes = BM * HC * 2;                 // 16384 per buffer
 constexpr int kThreads = 64 + 32 * 8;
@@ -68,8 +69,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int s = 0; s < kSlots; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], CM);
     mbar_init(a_full, 1), mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&hacc_full[b], 1), mbar_init(&hacc_empty[b], 8);
-      mbar_init(&hs_full[b], 8), mbar_init(&hs_empty[b], 1);
+      mbar_init(&hacc_full[b], 1), mbar_init(&hacc_empty[b], 4);  // buffer b is served by epilogue group b (4 warps)
+      mbar_init(&hs_full[b], 4), mbar_init(&hs_empty[b], 1);
     }
     mbar_init(y_full, 1), mbar_init(y_empty, 8);
     fence_mbar_init();
@@ -94,7 +95,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(a_empty, tphase ^ 1);
         mbar_arrive_expect_tx(a_full, kABytes);
         for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(sA + kb * 16384, &tmX, a_full, kb * 64, tm * BM);
-        for (int j = 0; j <= NCH; ++j) {
+        for (int j = 0; j < NCH + kLag; ++j) {
           if (j < NCH) {  // W1 rows [64j, 64j+64): two half-slices of 3 k-blocks
             for (int hf = 0; hf < 2; ++hf) {
               mbar_wait(&w_empty[slot], wphase ^ 1);
@@ -111,15 +112,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               next();
             }
           }
-          if (j >= 1) {  // W2[:, 64(j-1) : 64j): two N-halves of 192 rows
+          if (j >= kLag) {  // W2[:, 64(j-kLag) : +64): two N-halves of 192 rows
             for (int nh = 0; nh < 2; ++nh) {
               mbar_wait(&w_empty[slot], wphase ^ 1);
               mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
               uint8_t* dst = sW + slot * kSlotBytes;
               if (CM == 1) {
-                tma_load_2d(dst, &tmW2, &w_full[slot], (j - 1) * HC, nh * 192);
+                tma_load_2d(dst, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192);
               } else {
-                tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], (j - 1) * HC, nh * 192 + rank * 96, kMask);
+                tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192 + rank * 96, kMask);
               }
               next();
             }
@@ -142,7 +143,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int t = cluster_id; t < super_m; t += num_clusters) {
         mbar_wait(a_full, tphase);
         tc_fence_after();
-        for (int j = 0; j <= NCH; ++j) {
+        for (int j = 0; j < NCH + kLag; ++j) {
           if (j < NCH) {
             const int b = j & 1;
             mbar_wait(&hacc_empty[b], hacc_ph[b] ^ 1);  // epilogue done with the previous use of TMEM H[b]
@@ -165,8 +166,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             hacc_ph[b] ^= 1;
             if (j == NCH - 1) umma_commit(a_empty);  // x tile no longer needed once these MMAs retire
           }
-          if (j >= 1) {
-            const int jj = j - 1, b = jj & 1;
+          if (j >= kLag) {  // GEMM2 trails GEMM1 by kLag chunks so the tensor pipe has work while GELU(H) is produced
+            const int jj = j - kLag, b = jj & 1;
             mbar_wait(&hs_full[b], hs_ph[b]);  // GELU(H_jj) is in shared memory
             hs_ph[b] ^= 1;
             if (jj == 0) mbar_wait(y_empty, tphase ^ 1);  // previous tile's Y has been read out
@@ -192,41 +193,51 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;  // `half` doubles as the epilogue group id (= H buffer it serves)
     const int r_in_tile = quarter * 32 + lane;
-    uint32_t hacc_ph[2] = {0, 0}, hs_ph[2] = {0, 0}, tphase = 0;
-    uint8_t* my_store = sH + (warp - 2) * 4096;  // staging reuses the H buffers once the tile's GEMM2s are done
+    uint32_t hacc_phase = 0, hs_phase = 0, tphase = 0;
+    // Output staging reuses the H buffers once the tile's GEMM2s are done.  Each warp stages inside the 4 KB slice of
+    // H[half] that holds ITS OWN rows (32 rows x 128 B), so the next tile's GELU writes -- which only it performs, after
+    // its own bulk-store reads have drained -- can never overwrite another warp's pending store.
+    uint8_t* my_store = sH + half * kHBytes + quarter * 4096;
     for (int t = cluster_id; t < super_m; t += num_clusters) {
       const int tm = t * CM + rank;
-      for (int j = 0; j < NCH; ++j) {
-        const int b = j & 1;
-        mbar_wait(&hacc_full[b], hacc_ph[b]);
-        hacc_ph[b] ^= 1;
+      // group g (4 warps = 128 rows) owns the chunks j = g, g + 2, ...: two chunks are in flight, so the TMEM-load /
+      // barrier latencies of one overlap the GELU arithmetic of the other
+      for (int j = half; j < NCH; j += 2) {
+        const int b = half;
+        mbar_wait(&hacc_full[b], hacc_phase);
+        hacc_phase ^= 1;
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld32(tmem + (uint32_t(quarter * 32) << 16) + 384 + b * HC + half * 32, r);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem + (uint32_t(quarter * 32) << 16) + 384 + b * HC, r0);
+        tmem_ld32(tmem + (uint32_t(quarter * 32) << 16) + 384 + b * HC + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hacc_empty[b]);
-        const float* bias = args.b1 + j * HC + half * 32;
-        uint32_t pk[16];
+        const float* bias = args.b1 + j * HC;
+        uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-          pk[c / 2] = pack_bf16(gelu_erf(__uint_as_float(r[c]) + bb.x), gelu_erf(__uint_as_float(r[c + 1]) + bb.y));
-          pk[c / 2 + 1] = pack_bf16(gelu_erf(__uint_as_float(r[c + 2]) + bb.z), gelu_erf(__uint_as_float(r[c + 3]) + bb.w));
+        for (int c = 0; c < 64; c += 8) {
+          const uint32_t* rr = c < 32 ? r0 + c : r1 + (c - 32);
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + c));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+          float g[8] = {__uint_as_float(rr[0]) + ba.x, __uint_as_float(rr[1]) + ba.y, __uint_as_float(rr[2]) + ba.z,
+                        __uint_as_float(rr[3]) + ba.w, __uint_as_float(rr[4]) + bb.x, __uint_as_float(rr[5]) + bb.y,
+                        __uint_as_float(rr[6]) + bb.z, __uint_as_float(rr[7]) + bb.w};
+          gelu_erf8(g);
+          pk[c / 2] = pack_bf16(g[0], g[1]), pk[c / 2 + 1] = pack_bf16(g[2], g[3]);
+          pk[c / 2 + 2] = pack_bf16(g[4], g[5]), pk[c / 2 + 3] = pack_bf16(g[6], g[7]);
         }
-        mbar_wait(&hs_empty[b], hs_ph[b] ^ 1);  // GEMM2(j-2) has finished reading this buffer
-        hs_ph[b] ^= 1;
+        mbar_wait(&hs_empty[b], hs_phase ^ 1);  // GEMM2(j-2) has finished reading this buffer
+        hs_phase ^= 1;
         // K-major, 128-byte swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r % 8)) of its 128-byte row
         uint8_t* row = sH + b * kHBytes + (r_in_tile >> 3) * 1024 + (r_in_tile & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = half * 4 + c;
-          *reinterpret_cast<uint4*>(row + ((chunk ^ (r_in_tile & 7)) << 4)) =
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(row + ((c ^ (r_in_tile & 7)) << 4)) =
               make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hs_full[b]);

@@ -277,7 +277,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (args.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; j += 8) {
+            float g[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
+            gelu_erf8(g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j + i] = g[i];
+          }
         } else if (args.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);

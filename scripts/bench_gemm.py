@@ -36,3 +36,22 @@ for M, N, K, act in SHAPES:
     fl = 2.0 * M * N * K
     print("M=%6d N=%6d K=%6d act=%d  n1 %7.1f us %7.1f TF/s | cublas %7.1f us %7.1f TF/s | ratio %.2f" %
           (M, N, K, act, t_n1 * 1e3, fl / t_n1 / 1e9, t_cb * 1e3, fl / t_cb / 1e9, t_cb / t_n1))
+
+# fused NavDP MLP (384 -> 1536 -> 384 + residual) vs the two-GEMM path
+for M in (65536, 2048):
+    x = torch.randn(M, 384, device="cuda").bfloat16()
+    w1 = (torch.randn(1536, 384, device="cuda") / 384 ** 0.5).bfloat16()
+    w2 = (torch.randn(384, 1536, device="cuda") / 1536 ** 0.5).bfloat16()
+    b1, b2 = torch.randn(1536, device="cuda"), torch.randn(384, device="cuda")
+    res = torch.randn(M, 384, device="cuda").bfloat16()
+    hid = torch.empty(M, 1536, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(M, 384, device="cuda", dtype=torch.bfloat16)
+
+    def two():
+        _lib.gemm(x, w1, bias=b1, act=1, out=hid)
+        _lib.gemm(hid, w2, bias=b2, residual=res, out=out)
+    fl = 4.0 * M * 384 * 1536
+    for name, fn in (("two GEMMs", two), ("fused cm1", lambda: _lib.fused_mlp(x, w1, b1, w2, b2, residual=res, out=out, cluster=1)),
+                     ("fused cm2", lambda: _lib.fused_mlp(x, w1, b1, w2, b2, residual=res, out=out, cluster=2))):
+        t = timeit(fn)
+        print("MLP M=%6d %-10s %7.1f us %7.1f TF/s" % (M, name, t * 1e3, fl / t / 1e9))

@@ -1,5 +1,6 @@
 """Kernel-level parity (through the C ABI) against fp32 PyTorch references of the same op."""
 import math
+import os
 
 import pytest
 import torch
@@ -197,6 +198,8 @@ def test_attention_varlen(L):
             s += n
 
 
+@pytest.mark.skipif(os.environ.get("N1_TEST_EXPERIMENTAL") != "1",
+                    reason="fused MLP kernel is experimental and disabled by default (see fused_mlp.cu / DESIGN.md)")
 @pytest.mark.parametrize("M,cluster", [(128, 1), (1000, 1), (256, 2), (1000, 2), (65536 // 8, 2), (300, 2)])
 def test_fused_mlp(L, M, cluster):
     torch.manual_seed(M)
