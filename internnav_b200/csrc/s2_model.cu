@@ -287,11 +287,11 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
   const long T = p.tokens;
   const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd;
   bf16* x = c.take<bf16>(T * H);
-  bf16* ln = c.take<bf16>(T * H);
+  const long sel_rows = 3L * p.B * p.n_query;  // the last layer reuses `ln` for three [B * n_query, H] buffers
+  bf16* ln = c.take<bf16>((T > sel_rows ? T : sel_rows) * H);
   bf16* qkv = c.take<bf16>(T * qkv_n);
   bf16* att = c.take<bf16>(T * H);
   bf16* hid = c.take<bf16>(T * (long)inter_pad_);
-  bf16* sel = c.take<bf16>((long)p.B * p.n_query * H);
   if (c.dry()) return c.used();
 
   build_embeds(p.kind, p.src, embed_, image_feats, latentq_, x, T, H, s);
@@ -309,6 +309,27 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
     attention(a, s);
     GemmEpilogue res;
     res.residual = x, res.ldr = H;
+    if (l == dims.layers - 1) {
+      // Only the n_query TRAJ rows of each sequence are read after the last layer (internvla_n1.py L345): every token
+      // still contributes K/V to the attention above, but o_proj and the MLP run on those B * n_query rows alone.
+      const int R = p.B * p.n_query;
+      bf16* att_sel = ln;                      // [R, H] scratch (ln is free here)
+      bf16* x_sel = ln + (long)R * H;          // [R, H]
+      bf16* ln_sel = ln + 2L * R * H;          // [R, H]
+      gather_rows(att, p.out_rows, att_sel, R, 1, H, s);
+      gather_rows(x, p.out_rows, x_sel, R, 1, H, s);
+      GemmEpilogue rs;
+      rs.residual = x_sel, rs.ldr = H;
+      linear(b.o, att_sel, H, x_sel, H, R, rs, s);
+      layernorm(x_sel, H, ln_sel, H, b.n2, nullptr, R, H, dims.rms_eps, 1, s);
+      GemmEpilogue sw;
+      sw.act = ACT_SWIGLU;
+      linear(b.gateup, ln_sel, H, hid, inter_pad_, R, sw, s);
+      linear(b.down, hid, inter_pad_, x_sel, H, R, rs, s);
+      // outputs.hidden_states[-1][:, -N_QUERY:, :] -- the last entry is post final-norm
+      layernorm(x_sel, H, out, H, final_norm_, nullptr, R, H, dims.rms_eps, 1, s);
+      break;
+    }
     linear(b.o, att, H, x, H, (int)T, res, s);
     layernorm(x, H, ln, H, b.n2, nullptr, (int)T, H, dims.rms_eps, 1, s);
     GemmEpilogue sw;
@@ -316,9 +337,6 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
     linear(b.gateup, ln, H, hid, inter_pad_, (int)T, sw, s);
     linear(b.down, hid, inter_pad_, x, H, (int)T, res, s);
   }
-  // outputs.hidden_states[-1][:, -N_QUERY:, :] -- the last entry is post final-norm (internvla_n1.py L345)
-  gather_rows(x, p.out_rows, sel, (long)p.B * p.n_query, 1, H, s);
-  layernorm(sel, H, out, H, final_norm_, nullptr, p.B * p.n_query, H, dims.rms_eps, 1, s);
   return c.used();
 }
 
