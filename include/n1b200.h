@@ -169,6 +169,12 @@ int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, in
 int n1_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, void* out, int ldo, int M, int N, int K,
                const float* bias, const float* gamma, const void* residual_bf16, int ldr, int act, int out_fp32,
                void* stream);
+/* Full-row GEMM, N = 384: out = [gamma *] (A @ W^T + bias) + residual, and (ln_out != NULL) ln_out = LayerNorm(out).
+ * Replaces out_proj / linear2 + residual followed by the next LayerNorm of the NavDP decoder layer (navdp.py L57-66).
+ * out must not alias residual when ln_out is given. */
+int n1_op_gemm_row384(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int K, const float* bias,
+                      const float* gamma, const void* residual_bf16, int ldr, void* out_bf16, int ldo,
+                      const float* ln_w, const float* ln_b, float ln_eps, void* ln_out_bf16, int ld_ln, void* stream);
 /* NavDP decoder FF block in one kernel: out = residual + W2 GELU(W1 x + b1) + b2; x [M,384], W1 [1536,384], W2 [384,1536]
  * (replaces linear1 / gelu / linear2 / residual of nn.TransformerDecoderLayer, navdp.py L57-66).  cluster: 1 or 2. */
 int n1_op_fused_mlp(const void* x_bf16, int ldx, const void* w1_bf16, const float* b1, const void* w2_bf16,

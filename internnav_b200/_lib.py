@@ -57,6 +57,8 @@ SYMBOLS = {
                              ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_void_p]),
+    "n1_op_gemm_row384": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     "n1_op_fused_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                 c_int, c_int, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
@@ -173,3 +175,18 @@ def fused_mlp(x, w1, b1, w2, b2, residual=None, out=None, cluster=2):
                                 residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
                                 out.stride(0), x.shape[0], cluster, stream_ptr()))
     return out
+
+
+def gemm_row384(a, w, bias, gamma=None, residual=None, ln_w=None, ln_b=None, eps=1e-5, out=None):
+    """out = [gamma *] (a @ w.T + bias) + residual (N = 384); with ln_w also returns LayerNorm(out) * ln_w + ln_b."""
+    assert a.dtype == torch.bfloat16 and w.shape[0] == 384 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    if out is None:
+        out = torch.empty(M, 384, device=a.device, dtype=torch.bfloat16)
+    ln_out = torch.empty(M, 384, device=a.device, dtype=torch.bfloat16) if ln_w is not None else None
+    check(lib().n1_op_gemm_row384(c_void_p(a.data_ptr()), a.stride(0), c_void_p(w.data_ptr()), w.stride(0), M, K,
+                                  ptr(bias), ptr(gamma), c_void_p(residual.data_ptr()) if residual is not None else None,
+                                  residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
+                                  out.stride(0), ptr(ln_w), ptr(ln_b), eps, ptr(ln_out),
+                                  ln_out.stride(0) if ln_out is not None else 0, stream_ptr()))
+    return (out, ln_out) if ln_out is not None else out

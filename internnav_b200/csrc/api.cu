@@ -327,6 +327,15 @@ int n1_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ld
   });
 }
 
+int n1_op_gemm_row384(const void* A, int lda, const void* W, int ldw, int M, int K, const float* bias, const float* gamma,
+                      const void* residual, int ldr, void* out, int ldo, const float* ln_w, const float* ln_b,
+                      float ln_eps, void* ln_out, int ld_ln, void* stream) {
+  return guard([&] {
+    gemm_row384(B16(A), lda, B16(W), ldw, M, K, bias, gamma, B16(residual), ldr, B16(out), ldo, ln_w, ln_b, ln_eps,
+                B16(ln_out), ld_ln, S(stream));
+  });
+}
+
 int n1_op_fused_mlp(const void* x, int ldx, const void* w1, const float* b1, const void* w2, const float* b2,
                     const void* residual, int ldr, void* out, int ldo, int M, int cluster, void* stream) {
   return guard([&] {

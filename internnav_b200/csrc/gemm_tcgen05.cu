@@ -484,6 +484,16 @@ std::vector<EvPair> g_events;
 
 }  // namespace
 
+CUtensorMap tma_map_2d(const bf16* ptr, long rows, long cols, long ld, int box_rows, int box_cols, bool swizzle) {
+  return make_map(ptr, rows, cols, ld, box_rows, box_cols, swizzle);
+}
+// GEMM-class kernels in other files: counted like gemm_bf16 launches (event timing is only done for gemm_bf16)
+void prof_count_gemm(double flops) {
+  (void)flops;
+  g_gemm_launches++;
+  g_total_launches++;
+}
+
 void prof_enable(bool on) { g_prof_on = on; }
 void prof_count_launch(int n) { g_total_launches += n; }
 ProfStats prof_read_and_reset() {

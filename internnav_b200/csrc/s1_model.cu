@@ -32,6 +32,19 @@ void linear(const Lin& L, const bf16* A, int lda, void* out, int ldo, int M, Gem
   gemm_bf16(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, s);
 }
 
+// N1_ROW384: 1 = residual GEMMs of the decoder use the full-row kernel with fused LayerNorm (gemm_row384.cu),
+// 0 (default) = generic GEMM + LayerNorm kernels.  The fused kernel is correct (tests/test_ops_gpu.py) but measured
+// slower on B200 (182 vs 152 us at 65536 x 1536, 67 vs 43 us at 65536 x 384): its single accumulator stage exposes the
+// epilogue, whose per-row residual loads are latency-bound.  Kept for the next round.
+int row384_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("N1_ROW384");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
 // N1_FUSED_MLP: 0 (default) = two GEMMs, 1 = fused kernel, 2 = fused kernel with 2-CTA weight multicast.
 // The fused kernel (fused_mlp.cu) is EXPERIMENTAL and off: it is correct when it completes, but it is slower than the
 // two-GEMM path (GELU issue-bound, ~400 vs ~320 us at 65536 rows) and a rare hang was seen under pytest on B200.
@@ -381,7 +394,7 @@ void S1Model::goal_compress(void* ws, size_t ws_bytes, const bf16* latents, bf16
 
 // ------------------------------------------------------------------------------------------------ denoiser
 struct S1Model::DenoiseBufs {
-  bf16 *x, *ln, *qkv, *att, *hid, *cond, *ckv;
+  bf16 *x, *x2, *ln, *qkv, *att, *hid, *cond, *ckv;
 };
 
 S1Model::DenoiseBufs S1Model::carve_denoise(Carver& c, int B, int Ns, int T) const {
@@ -389,6 +402,7 @@ S1Model::DenoiseBufs S1Model::carve_denoise(Carver& c, int B, int Ns, int T) con
   const long R = (long)B * Ns * T;
   DenoiseBufs d;
   d.x = c.take<bf16>(R * D);
+  d.x2 = c.take<bf16>(R * D);  // ping-pong partner of x for the fused GEMM + LayerNorm (no in-place update there)
   d.ln = c.take<bf16>(R * D);
   d.qkv = c.take<bf16>(R * 3 * D);
   d.att = c.take<bf16>(R * D);
@@ -416,9 +430,29 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     linear(kv_all_, d.cond, Mtok * D, d.ckv, Mtok * ldkv, B, GemmEpilogue(), s);
   }
   const float scale48 = 1.0f / sqrtf(48.f);
+  bf16* xc = d.x;   // current residual stream
+  bf16* xo = d.x2;  // the other buffer
+  const bool fuse_ln = row384_mode() > 0;
+  // residual GEMM (N = 384) + the LayerNorm that follows it, in one kernel when enabled (gemm_row384.cu)
+  auto res_gemm_ln = [&](const Lin& W, const bf16* A, int lda, const LNp* ln) {
+    if (fuse_ln) {
+      if (ln) {
+        gemm_row384(A, lda, W.w, W.ldw, (int)R, W.K, W.b, nullptr, xc, D, xo, D, ln->w, ln->b, 1e-5f, d.ln, D, s);
+        bf16* t = xc;
+        xc = xo, xo = t;
+      } else {
+        gemm_row384(A, lda, W.w, W.ldw, (int)R, W.K, W.b, nullptr, xc, D, xc, D, nullptr, nullptr, 0.f, nullptr, 0, s);
+      }
+    } else {
+      GemmEpilogue res;
+      res.residual = xc, res.ldr = D;
+      linear(W, A, lda, xc, D, (int)R, res, s);
+      if (ln) layernorm(xc, D, d.ln, D, ln->w, ln->b, (int)R, D, 1e-5f, 0, s);
+    }
+  };
+  layernorm(xc, D, d.ln, D, dec_[0].n1.w, dec_[0].n1.b, (int)R, D, 1e-5f, 0, s);
   for (int l = 0; l < dims.layers; ++l) {
     const DecLayer& L = dec_[l];
-    layernorm(d.x, D, d.ln, D, L.n1.w, L.n1.b, (int)R, D, 1e-5f, 0, s);
     linear(L.sa_qkv, d.ln, D, d.qkv, 3 * D, (int)R, GemmEpilogue(), s);
     AttnParams p = {};
     p.q = d.qkv, p.k = d.qkv + D, p.v = d.qkv + 2 * D, p.o = d.att;
@@ -426,11 +460,8 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     p.heads_q = p.heads_kv = dims.heads, p.hd = 48, p.batch = B * Ns, p.seq_q = p.seq_k = T, p.kv_div = 1;
     p.causal = 1, p.scale = scale48;
     attention(p, s);
-    GemmEpilogue res;
-    res.residual = d.x, res.ldr = D;
-    linear(L.sa_out, d.att, D, d.x, D, (int)R, res, s);
+    res_gemm_ln(L.sa_out, d.att, D, &L.n2);
 
-    layernorm(d.x, D, d.ln, D, L.n2.w, L.n2.b, (int)R, D, 1e-5f, 0, s);
     linear(L.ca_q, d.ln, D, d.qkv, D, (int)R, GemmEpilogue(), s);
     AttnParams pc = {};
     pc.q = d.qkv, pc.k = d.ckv + (long)l * 2 * D, pc.v = d.ckv + (long)l * 2 * D + D, pc.o = d.att;
@@ -438,20 +469,20 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     pc.heads_q = pc.heads_kv = dims.heads, pc.hd = 48, pc.batch = B * Ns, pc.seq_q = T, pc.seq_k = Mtok;
     pc.kv_div = Ns, pc.scale = scale48;
     attention(pc, s);
-    linear(L.ca_out, d.att, D, d.x, D, (int)R, res, s);
+    res_gemm_ln(L.ca_out, d.att, D, &L.n3);
 
-    layernorm(d.x, D, d.ln, D, L.n3.w, L.n3.b, (int)R, D, 1e-5f, 0, s);
+    const LNp* next_ln = l + 1 < dims.layers ? &dec_[l + 1].n1 : nullptr;  // the head applies the final LayerNorm itself
     if (fused_mlp_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536) {
-      // FF block in one kernel: the [R, 1536] hidden never leaves the SM (fused_mlp.cu)
-      fused_mlp_384(d.ln, D, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, d.x, D, d.x, D, (int)R, fused_mlp_mode(), s);
+      fused_mlp_384(d.ln, D, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, xc, D, xc, D, (int)R, fused_mlp_mode(), s);
+      if (next_ln) layernorm(xc, D, d.ln, D, next_ln->w, next_ln->b, (int)R, D, 1e-5f, 0, s);
     } else {
       GemmEpilogue gelu;
       gelu.act = ACT_GELU;
       linear(L.ff1, d.ln, D, d.hid, 4 * D, (int)R, gelu, s);
-      linear(L.ff2, d.hid, 4 * D, d.x, D, (int)R, res, s);
+      res_gemm_ln(L.ff2, d.hid, 4 * D, next_ln);
     }
   }
-  head_ddpm(d.x, final_ln_.w, final_ln_.b, head_w_, head_b_, R, mode, x_io, noise, eps, cf, s);
+  head_ddpm(xc, final_ln_.w, final_ln_.b, head_w_, head_b_, R, mode, x_io, noise, eps, cf, s);
 }
 
 size_t S1Model::ws_denoise(int B, int Ns, int T) const {

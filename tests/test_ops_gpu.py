@@ -216,3 +216,27 @@ def test_fused_mlp(L, M, cluster):
     r2 = res.clone()
     L.fused_mlp(x, w1, b1, w2, b2, residual=r2, out=r2, cluster=cluster)
     assert _rel(r2, ref) < 8e-3
+
+
+@pytest.mark.parametrize("M,K,use_ln,use_gamma", [(128, 384, False, False), (300, 384, True, True), (1000, 1536, True, False),
+                                                  (4096, 384, True, False)])
+def test_gemm_row384(L, M, K, use_ln, use_gamma):
+    """Full-row N = 384 GEMM with fused residual / layer-scale / LayerNorm (experimental path, off by default)."""
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(384, K, device="cuda") / math.sqrt(K)).bfloat16()
+    bias = torch.randn(384, device="cuda") * 0.1
+    gamma = torch.randn(384, device="cuda") if use_gamma else None
+    res = torch.randn(M, 384, device="cuda").bfloat16()
+    y = a.float() @ w.float().T + bias
+    if gamma is not None:
+        y = y * gamma
+    y = y + res.float()
+    if use_ln:
+        lw, lb = 1 + 0.1 * torch.randn(384, device="cuda"), 0.1 * torch.randn(384, device="cuda")
+        out, ln = L.gemm_row384(a, w, bias, gamma=gamma, residual=res, ln_w=lw, ln_b=lb)
+        ref_ln = torch.nn.functional.layer_norm(y.bfloat16().float(), (384,), lw, lb, 1e-5)
+        assert _rel(out, y) < 6e-3 and _rel(ln, ref_ln) < 6e-3
+    else:
+        out = L.gemm_row384(a, w, bias, gamma=gamma, residual=res)
+        assert _rel(out, y) < 6e-3
