@@ -65,7 +65,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.25)
 
     def __enter__(self):
         self.t.start()
