@@ -203,8 +203,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int tm, tn;
       decode_tile(tile, super_m, args.tiles_n, tm, tn);
       tm = tm * CM + rank;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = tm * BM + quarter * 32 + lane;
       const bool row_ok = row < args.M;
       long out_row = row;
@@ -213,11 +211,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         grp_row = row % args.rows_per_group;
         out_row = (long)(row / args.rows_per_group) * args.group_stride + grp_row + args.group_offset;
       }
+      // Residual tile: per-row 16-byte loads whose latency dominated the epilogue of the short-K GEMMs
+      // (profiles/r1_ncu_gemm384_v3_summary.txt).  They do not depend on the accumulator, so the loads of chunk c + 2
+      // are issued while chunk c is processed, and those of the first chunk before the accumulator wait.
+      const bool use_res = args.residual != nullptr && row_ok && !swiglu;
+      uint4 res_next[4];
+      auto prefetch_res = [&](int chunk) {
+        const int c0 = tn * BN + chunk * 32;
+        const bf16* rr = args.residual + out_row * args.ldr + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          res_next[j] = (use_res && c0 + j * 8 < args.N) ? __ldg(reinterpret_cast<const uint4*>(rr + j * 8))
+                                                         : make_uint4(0u, 0u, 0u, 0u);
+      };
+      prefetch_res(half);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int chunk = half; chunk < BN / 32; chunk += 2) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + chunk * 32, r);
+        const uint4 res_cur[4] = {res_next[0], res_next[1], res_next[2], res_next[3]};
+        if (chunk + 2 < BN / 32) prefetch_res(chunk + 2);
         tmem_ld_wait();
         const int col0 = tn * BN + chunk * 32;
         if (col0 >= args.N) continue;  // warp-uniform
@@ -308,11 +324,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         if (args.residual) {
-          const bf16* rr = args.residual + out_row * args.ldr + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < args.N) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rr + j));
+              const uint4 q = res_cur[j >> 3];
               v[j + 0] += bf16_lo(q.x), v[j + 1] += bf16_hi(q.x);
               v[j + 2] += bf16_lo(q.y), v[j + 3] += bf16_hi(q.y);
               v[j + 4] += bf16_lo(q.z), v[j + 5] += bf16_hi(q.z);
