@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
 // single-pass softmax and PV for its head on mma.sync; O is staged back through the Q tile and written coalesced.
 // The generic kernel above spent 4x the work on padding at these shapes (profiles/r1_ncu_small_v0_summary.txt).
 template <int NKP>  // key tiles of 16
-__global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p, const int G) {
   constexpr int HD = 48;
   extern __shared__ __align__(16) uint8_t ssm[];
   const int heads = p.heads_q;
@@ -245,16 +245,21 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p) {
   uint8_t* sQ = ssm;
   uint8_t* sK = sQ + sq_pad * RS;
   uint8_t* sV = sK + sk_pad * RS;
-  const int b = blockIdx.x;
-  const int kb = b / p.kv_div;
-  const bf16* gq = p.q + (long)b * sq * p.ldq;
+  // G consecutive query sequences that share one K/V sequence (G divides kv_div) are handled by one CTA: K/V is
+  // staged once, Q / O tiles are cycled through the same buffer.
+  const int b0 = blockIdx.x * G;
+  const int kb = b0 / p.kv_div;
   const bf16* gk = p.k + (long)kb * sk * p.ldk;
   const bf16* gv = p.v + (long)kb * sk * p.ldv;
   const int chunks = heads * HD / 8;  // 16-byte chunks per row
-  for (int c = threadIdx.x; c < sq_pad * chunks; c += blockDim.x) {
-    const int r = c / chunks, ch = c % chunks;
-    cp_async16(sQ + r * RS + ch * 16, gq + (long)(r < sq ? r : 0) * p.ldq + ch * 8, r < sq);
-  }
+  auto load_q = [&](int b) {
+    const bf16* gq = p.q + (long)b * sq * p.ldq;
+    for (int c = threadIdx.x; c < sq_pad * chunks; c += blockDim.x) {
+      const int r = c / chunks, ch = c % chunks;
+      cp_async16(sQ + r * RS + ch * 16, gq + (long)(r < sq ? r : 0) * p.ldq + ch * 8, r < sq);
+    }
+  };
+  load_q(b0);
   for (int c = threadIdx.x; c < sk_pad * chunks; c += blockDim.x) {
     const int r = c / chunks, ch = c % chunks;
     const bool ok = r < sk;
@@ -269,6 +274,14 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p) {
   const int lm = lane >> 3, lr = lane & 7;
   const float sl2 = p.scale * 1.4426950408889634f;
   const int causal_off = sk - sq;
+  for (int g = 0; g < G; ++g) {
+  const int b = b0 + g;
+  if (g > 0) {  // previous O tile has been written out (barrier at the end of the loop body): refill Q
+    load_q(b);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
   if (h < heads) {
     for (int mt = 0; mt < sq_pad / 16; ++mt) {
       uint32_t qf[3][4];
@@ -351,6 +364,8 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnParams p) {
     const int r = c / chunks, ch = c % chunks;
     *reinterpret_cast<uint4*>(go + (long)r * p.ldo + ch * 8) = *reinterpret_cast<const uint4*>(sQ + r * RS + ch * 16);
   }
+  __syncthreads();  // O tile drained before the next sequence's Q overwrites it
+  }  // g
 }
 
 template <int NKP>
@@ -362,7 +377,10 @@ void launch_attn_small(const AttnParams& p, cudaStream_t stream) {
     cudaFuncSetAttribute(attn_small_kernel<NKP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 + 2 * NKP * 16) * (8 * 96 + 16));
     attr_set = true;
   }
-  attn_small_kernel<NKP><<<p.batch, p.heads_q * 32, smem, stream>>>(p);
+  int G = 1;  // sequences per CTA: only when they share K/V
+  if (p.kv_div % 4 == 0 && p.batch % 4 == 0) G = 4;
+  else if (p.kv_div % 2 == 0 && p.batch % 2 == 0) G = 2;
+  attn_small_kernel<NKP><<<p.batch / G, p.heads_q * 32, smem, stream>>>(p, G);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }

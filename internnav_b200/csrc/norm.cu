@@ -73,6 +73,61 @@ __global__ void __launch_bounds__(256) norm_kernel(const bf16* __restrict__ x, i
   }
 }
 
+// D = 384 LayerNorm (the NavDP decoder / DINOv2 width): RPW rows per warp with all their loads issued up front (more
+// bytes in flight than one row per warp), 8-byte vectors so the 96 vectors of a row split evenly over the 32 lanes,
+// weights read once per warp.
+template <int RPW>
+__global__ void __launch_bounds__(256) ln384_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                                    const float* __restrict__ w, const float* __restrict__ b, int rows,
+                                                    float eps) {
+  constexpr int D = 384;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const long row0 = (long)warp * RPW;
+  if (row0 >= rows) return;
+  uint2 q[RPW][3];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      q[r][i] = (row0 + r < rows) ? *reinterpret_cast<const uint2*>(x + (row0 + r) * ldx + (lane + i * 32) * 4)
+                                  : make_uint2(0u, 0u);
+  float ww[12], bb[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w + (lane + i * 32) * 4));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(b + (lane + i * 32) * 4));
+    ww[i * 4] = a.x, ww[i * 4 + 1] = a.y, ww[i * 4 + 2] = a.z, ww[i * 4 + 3] = a.w;
+    bb[i * 4] = c.x, bb[i * 4 + 1] = c.y, bb[i * 4 + 2] = c.z, bb[i * 4 + 3] = c.w;
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    float v[12];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      v[i * 4] = bf16_lo(q[r][i].x), v[i * 4 + 1] = bf16_hi(q[r][i].x);
+      v[i * 4 + 2] = bf16_lo(q[r][i].y), v[i * 4 + 3] = bf16_hi(q[r][i].y);
+      s += v[i * 4] + v[i * 4 + 1] + v[i * 4 + 2] + v[i * 4 + 3];
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sq += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    if (row0 + r < rows) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        uint2 o;
+        o.x = pack_bf16((v[i * 4] - mean) * rstd * ww[i * 4] + bb[i * 4],
+                        (v[i * 4 + 1] - mean) * rstd * ww[i * 4 + 1] + bb[i * 4 + 1]);
+        o.y = pack_bf16((v[i * 4 + 2] - mean) * rstd * ww[i * 4 + 2] + bb[i * 4 + 2],
+                        (v[i * 4 + 3] - mean) * rstd * ww[i * 4 + 3] + bb[i * 4 + 3]);
+        *reinterpret_cast<uint2*>(y + (row0 + r) * ldy + (lane + i * 32) * 4) = o;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const float* b, int rows, int D, float eps,
@@ -81,6 +136,14 @@ void layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* w, const f
   N1_CHECK(D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "norm: D and leading dims must be multiples of 8");
   N1_CHECK(D <= 8 * 32 * 20, "norm: D too large");
   const int threads = 256;
+  if (D == 384 && !rms && b != nullptr) {
+    constexpr int RPW = 4;
+    const int warps = (rows + RPW - 1) / RPW;
+    ln384_kernel<RPW><<<(warps * 32 + threads - 1) / threads, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, eps);
+    prof_count_launch();
+    N1_CUDA(cudaGetLastError());
+    return;
+  }
   const int blocks = (rows * 32 + threads - 1) / threads;
   if (D <= 8 * 32 * 2)
     norm_kernel<2><<<blocks, threads, 0, stream>>>(x, ldx, y, ldy, w, b, rows, D, eps, rms);
