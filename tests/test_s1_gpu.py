@@ -145,3 +145,32 @@ def test_training_branch_forward_loss(env):
         ref = O.s1_training_loss(sd, hs.float(), imgs, deps, poses, vfn, noise, ts.cuda())
     print("s1 loss", float(loss), "oracle", float(ref))
     assert abs(float(loss) - float(ref)) / float(ref) < 2e-2
+
+
+def test_sampling_call_is_graph_capturable(env):
+    """The C ABI promises hot calls that neither allocate nor synchronise (include/n1b200.h): the whole K-step sampling
+    loop must be capturable in a CUDA graph and replay to the same result."""
+    from oracle import weights
+    m, sd, sdb = env
+    inp = weights.make_inputs(44, B=2, T=8, Ns=32, K=20)
+    goal, rgbd = inp["goal"].cuda().bfloat16(), inp["rgbd"].cuda().bfloat16()
+    x0, nz = inp["x_init"].cuda(), inp["step_noise"].cuda()
+    eager = m.sample(goal, rgbd, x0, nz).clone()  # also warms up every kernel variant (attribute calls are not capturable)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        m.sample(goal, rgbd, x0, nz)  # scratch for this stream
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = m.sample(goal, rgbd, x0, nz)
+    torch.cuda.synchronize()
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    x0.add_(0.25)  # graphs read their inputs by address: new values, same launch sequence
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, m.sample(goal, rgbd, x0, nz))
