@@ -169,9 +169,52 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
                                      _lib.ptr(rgbd), _lib.ptr(eps), B, Ns, T, _lib.stream_ptr()))
         return eps.to(last_actions.dtype)
 
-    def sample(self, goal_embed, rgbd_embed, x_init, step_noise, num_steps=None):
-        """The DDPM loop of navdp.py L242-253 as one C-ABI call.  x_init [B*Ns,T,3], step_noise [K-1,B*Ns,T,3]."""
+    GRAPH_MAX_ROWS = 16384  # below this many decoder rows the K-step loop is launch-bound: replay it as a CUDA graph
+
+    def sample(self, goal_embed, rgbd_embed, x_init, step_noise, num_steps=None, graph=None):
+        """The DDPM loop of navdp.py L242-253 as one C-ABI call.  x_init [B*Ns,T,3], step_noise [K-1,B*Ns,T,3].
+        `graph`: replay the call's launch sequence (thousands of short kernels) from a cached CUDA graph; default = only
+        in the launch-bound regime (small batches)."""
         K = num_steps or self.num_train_timesteps
+        if graph is None:
+            graph = x_init.shape[0] * x_init.shape[1] <= self.GRAPH_MAX_ROWS and not torch.cuda.is_current_stream_capturing()
+        if graph:
+            return self._sample_graphed(goal_embed, rgbd_embed, x_init, step_noise, K)
+        return self._sample_eager(goal_embed, rgbd_embed, x_init, step_noise, K)
+
+    def _sample_graphed(self, goal_embed, rgbd_embed, x_init, step_noise, K):
+        dev = self._device
+        key = (tuple(goal_embed.shape), tuple(x_init.shape), K, step_noise is None)
+        ent = getattr(self, "_graphs", None)
+        if ent is None:
+            ent = self._graphs = {}
+        hit = ent.get(key)
+        if hit is None:
+            st = dict(goal=torch.empty(goal_embed.shape, device=dev, dtype=torch.bfloat16),
+                      rgbd=torch.empty(rgbd_embed.shape, device=dev, dtype=torch.bfloat16),
+                      x0=torch.empty(x_init.shape, device=dev, dtype=torch.float32),
+                      nz=None if step_noise is None else torch.empty(step_noise.shape, device=dev, dtype=torch.float32))
+            for k, v in (("goal", goal_embed), ("rgbd", rgbd_embed), ("x0", x_init), ("nz", step_noise)):
+                if v is not None:
+                    st[k].copy_(v)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._sample_eager(st["goal"], st["rgbd"], st["x0"], st["nz"], K)  # warm-up: attributes, scratch of `side`
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    out = self._sample_eager(st["goal"], st["rgbd"], st["x0"], st["nz"], K)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            hit = ent[key] = (g, st, out, side)
+        g, st, out, _ = hit
+        for k, v in (("goal", goal_embed), ("rgbd", rgbd_embed), ("x0", x_init), ("nz", step_noise)):
+            if v is not None:
+                st[k].copy_(v, non_blocking=True)
+        g.replay()
+        return out.clone()
+
+    def _sample_eager(self, goal_embed, rgbd_embed, x_init, step_noise, K):
         B = goal_embed.shape[0]
         R, T, _ = x_init.shape
         Ns = R // B
