@@ -373,17 +373,18 @@ def run_ours_denoise(args, wl):
     ms_e2e = timed(step_e2e, args.steps, use_events=False)
     barrier()
 
-    # roofline pass for the dominant kernel (tcgen05 GEMM): per-launch CUDA events, NOT part of the timed runs above
+    # roofline pass for the dominant kernel (tcgen05 GEMM): per-launch CUDA events, NOT part of the timed runs above;
+    # eager launches here (the timed runs replay the same launch sequence from a CUDA graph)
     _lib.prof_read()
     _lib.prof_enable(True)
-    step_resident()
+    model.sample(d_goal, d_rgbd, d_x0, d_nz, num_steps=K, graph=False)
     torch.cuda.synchronize()
     prof = _lib.prof_read()
     _lib.prof_enable(False)
 
     launches["total_launches"] //= max(args.steps, 1)
     _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
-            {"samples_per_env": Ns, "horizon": T, "ddpm_steps": K, "weights": "random-init NavDP (98.8M params)",
+            {"samples_per_env": Ns, "launch_mode": "CUDA graph replay of the K-step loop (eager for the roofline pass)", "horizon": T, "ddpm_steps": K, "weights": "random-init NavDP (98.8M params)",
              "launches_are": "per step"},
             {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (h_goal, h_rgbd, h_x0, h_nz)),
              "d2h_bytes_per_step": R * T * 3 * 4,

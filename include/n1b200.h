@@ -161,6 +161,8 @@ int n1_vit_window_index(const int32_t* grid_thw_host, int n_img, int merge, int 
  * events on its stream (bench.py's roofline pass -- not for timed runs).  n1_prof_read synchronises, returns the sums
  * since the last read and resets them. */
 void n1_prof_enable(int on);
+/* add kernel launches that bypassed the launchers (a replayed CUDA graph of a captured n1_* call) to the counters */
+void n1_prof_add(int64_t gemm_launches, int64_t total_launches);
 int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* total_launches);
 
 /* ------------------------------------------------------------------------------------------------ kernel-level ops

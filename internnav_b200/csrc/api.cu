@@ -307,6 +307,12 @@ int n1_vit_window_index(const int32_t* grid, int n_img, int merge, int window, i
 
 void n1_prof_enable(int on) { prof_enable(on != 0); }
 
+void n1_prof_add(int64_t gemm_launches, int64_t total_launches) {
+  // a replayed CUDA graph launches the kernels captured in it without passing through the launchers: account for them
+  prof_count_launch((int)(total_launches - gemm_launches));
+  for (int64_t i = 0; i < gemm_launches; ++i) prof_count_gemm(0.0);
+}
+
 int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* total_launches) {
   return guard([&] {
     ProfStats st = prof_read_and_reset();

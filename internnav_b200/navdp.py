@@ -202,16 +202,20 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
             with torch.cuda.stream(side):
                 self._sample_eager(st["goal"], st["rgbd"], st["x0"], st["nz"], K)  # warm-up: attributes, scratch of `side`
                 side.synchronize()
+                before = _lib.prof_read()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
                     out = self._sample_eager(st["goal"], st["rgbd"], st["x0"], st["nz"], K)
+                nodes = _lib.prof_read()  # kernels captured into the graph = launches of every replay
+                _lib.lib().n1_prof_add(before["gemm_launches"], before["total_launches"])  # restore the running counters
             torch.cuda.current_stream(dev).wait_stream(side)
-            hit = ent[key] = (g, st, out, side)
-        g, st, out, _ = hit
+            hit = ent[key] = (g, st, out, side, nodes)
+        g, st, out, _, nodes = hit
         for k, v in (("goal", goal_embed), ("rgbd", rgbd_embed), ("x0", x_init), ("nz", step_noise)):
             if v is not None:
                 st[k].copy_(v, non_blocking=True)
         g.replay()
+        _lib.lib().n1_prof_add(nodes["gemm_launches"], nodes["total_launches"])
         return out.clone()
 
     def _sample_eager(self, goal_embed, rgbd_embed, x_init, step_noise, K):
