@@ -108,7 +108,7 @@ class InternVLAN1ForCausalLM:
         Returns (trajectories [32B, T, 3], list of B action lists (<= 4 non-zero ids each, [] => action -1))."""
         lat = self.generate_latents(input_ids, pixel_values, image_grid_thw)
         traj = self.generate_traj(lat, images_dp, depths_dp, x_init=x_init, step_noise=step_noise)
-        acts = [s1_action_list(a) for a in batched_traj_to_actions(traj, lat.shape[0])]
+        acts = [s1_action_list(a) for a in batched_traj_to_actions(traj, lat.shape[0], max_actions=4)]
         return traj, acts
 
     def s1_training_loss(self, traj_hidden_states, traj_images, traj_depths, traj_poses, video_frame_num, noise=None,
@@ -162,7 +162,7 @@ class InternVLAN1Net:
         with torch.no_grad():
             dp_actions = self.model.generate_traj(traj_latents=latent, images_dp=rgb, depths_dp=depth)
         B = latent.shape[0]
-        lists = batched_traj_to_actions(dp_actions, B) if self.continuous_traj else None
+        lists = batched_traj_to_actions(dp_actions, B, max_actions=4) if self.continuous_traj else None
         if lists is None:
             raise NotImplementedError("chunk_token sampling path: use postprocess.chunk_token on a chosen sample")
         outs = [S1Output(idx=s1_action_list(a)) for a in lists]

@@ -9,7 +9,9 @@ import numpy as np
 import torch
 
 
-def _discretise(trajectory, step_size=0.25, turn_angle_deg=15, lookahead=4):
+def _discretise(trajectory, step_size=0.25, turn_angle_deg=15, lookahead=4, max_actions=None):
+    """`max_actions`: stop once that many ids exist.  The loop only ever appends, so the first `max_actions` entries are
+    identical to those of the full run -- which is all `s1_step_latent` keeps (internvla_n1_policy.py L212-214)."""
     actions = []
     yaw = 0.0
     pos = trajectory[0]
@@ -20,6 +22,8 @@ def _discretise(trajectory, step_size=0.25, turn_angle_deg=15, lookahead=4):
         return (angle + np.pi) % (2 * np.pi) - np.pi
 
     while np.linalg.norm(pos - goal) > 0.2:
+        if max_actions is not None and len(actions) >= max_actions:
+            break
         dists = np.linalg.norm(trajectory - pos, axis=1)
         nearest_idx = np.argmin(dists)
         target = trajectory[min(nearest_idx + lookahead, len(trajectory) - 1)]
@@ -56,15 +60,16 @@ def traj_to_actions(dp_actions, use_discrate_action=True):
     return _discretise(traj) if use_discrate_action else traj
 
 
-def batched_traj_to_actions(dp_actions, num_envs, use_discrate_action=True):
-    """dp_actions [num_envs * Ns, T, 3] (not modified) -> list of per-environment action lists."""
+def batched_traj_to_actions(dp_actions, num_envs, use_discrate_action=True, max_actions=None):
+    """dp_actions [num_envs * Ns, T, 3] (not modified) -> list of per-environment action lists (optionally only their
+    first `max_actions` entries, see _discretise)."""
     a = dp_actions.detach().float().cpu().numpy().copy()
     a[:, :, :2] /= 4.0
     ns = a.shape[0] // num_envs
     out = []
     for e in range(num_envs):
         traj = _mean_trajectory(a[e * ns:(e + 1) * ns])
-        out.append(_discretise(traj) if use_discrate_action else traj)
+        out.append(_discretise(traj, max_actions=max_actions) if use_discrate_action else traj)
     return out
 
 

@@ -84,6 +84,8 @@ def test_traj_to_actions_golden_bit_exact():
         assert O.traj_to_actions(tr) == g                       # oracle restatement
         assert P.traj_to_actions(tr.clone()) == g               # product host code
         assert P.batched_traj_to_actions(tr, 1)[0] == g
+        # early-exit variant keeps exactly the entries s1_step_latent consumes
+        assert P.s1_action_list(P.batched_traj_to_actions(tr, 1, max_actions=4)[0]) == P.s1_action_list(g)
     # empty / degenerate trajectories: the reference returns [] -> action -1 upstream
     z = torch.zeros(32, 8, 3)
     assert O.traj_to_actions(z) == [] and P.traj_to_actions(z.clone()) == []
