@@ -1,0 +1,63 @@
+"""End-to-end dual-system step through the model-level mirror class (tiny Qwen config + full-size NavDP head):
+System-2 latents -> System-1 trajectories -> action ids, against the oracle chain on the same weights and noise."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_dual_system_step_matches_oracle_chain():
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM, InternVLAN1Net
+    from internnav_b200.manifest import random_navdp_state_dict
+    from oracle import navdp_oracle as O, qwen_oracle as Q, weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = Q.tiny_cfg()  # hidden 256 -> NavDP vlm_token_dim 256
+    s2_sd = Q.make_s2_state_dict(cfg, seed=3, vocab_rows=512)
+    s1_sd = random_navdp_state_dict(seed=4, vlm_token_dim=cfg["hidden"])
+    model = InternVLAN1ForCausalLM(cfg, device="cuda:0")
+    model.load_parts(s2_sd, s1_sd)
+    assert model.get_n_query() == 4 and model.get_system1_type() == "navdp_async"
+    with pytest.raises(NotImplementedError):
+        model.generate()
+
+    B = 2
+    rng = np.random.Generator(np.random.PCG64(8))
+    gpp = [[(1, 16, 16)], [(1, 8, 12), (1, 16, 16)]]
+    prompts = [Q.make_prompt(rng, 9, gs, 21) for gs in gpp]
+    grids = [g for gs in gpp for g in gs]
+    n_p = sum(t * h * w for t, h, w in grids)
+    g = torch.Generator().manual_seed(2)
+    px = torch.randn(n_p, 1176, generator=g).bfloat16().cuda()
+    inp = weights.make_inputs(9, B=B, K=20)
+    rgb, dep = inp["rgb"].cuda(), inp["depth"].cuda()
+    x0, nz = inp["x_init"].cuda(), inp["step_noise"].cuda()
+
+    traj, acts = model.dual_system_step(prompts, px, grids, rgb, dep, x_init=x0, step_noise=nz)
+    assert traj.shape == (B * 32, 32, 3) and len(acts) == B and all(len(a) <= 4 for a in acts)
+
+    # oracle chain (fp32, on the GPU for speed): per-env generate_latents, then the batched System-1 oracle
+    s2_gpu = {k: v.cuda() for k, v in s2_sd.items()}
+    s1_gpu = {k: v.cuda().float() for k, v in s1_sd.items()}
+    lat, off = [], 0
+    with torch.no_grad():
+        for ids, gs in zip(prompts, gpp):
+            npb = sum(t * h * w for t, h, w in gs)
+            lat.append(Q.generate_latents(s2_gpu, cfg, torch.tensor([ids]), px[off:off + npb].float(), gs))
+            off += npb
+        lat = torch.cat(lat)
+        mine_lat = model.generate_latents(prompts, px, grids)
+        assert _rel(mine_lat, lat) < 2e-2
+        ref = O.predict_pointgoal_action_async(s1_gpu, lat, rgb, dep, x0, nz, K=20)
+    e = _rel(traj, ref)
+    print("dual-system trajectories rel err vs oracle chain", e)
+    assert e < 4e-2
+    # policy wrapper: same trajectories -> same ids as the batched tail
+    pol = InternVLAN1Net(model)
+    outs = pol.s1_step_latent(rgb, dep, mine_lat)
+    assert len(outs) == B and all(isinstance(o.idx, list) for o in outs)
