@@ -523,17 +523,69 @@ def run_reference(args, wl):
     print(json.dumps(out))
 
 
+def run_eager_gpu(args, wl):
+    """--impl eager: BASELINE arm, not the product -- the reference algorithm (oracle restatement, the same eager
+    PyTorch ops the reference issues) executed on the GPU in bf16 with batch = 1 per call, exactly how the reference
+    drives the model.  This is the "PyTorch-eager on the same B200" denominator of north_star's >= 10x
+    target.  Reported as policy-steps/s of one process stepping environments one after another."""
+    import numpy as np
+    from internnav_b200.manifest import random_navdp_state_dict, random_s2_state_dict
+    from oracle import navdp_oracle as O, qwen_oracle as Q
+    assert wl["kind"] == "dual", "--impl eager is defined for the dual_system workload"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = dict(Q.QWEN25VL_7B)
+    sd2 = random_s2_state_dict(cfg, seed=0, device=str(dev))
+    sd1 = {k: v.to(dev, torch.bfloat16) for k, v in random_navdp_state_dict(seed=0).items()}
+    t, h, w = wl["grid"]
+    rng = np.random.Generator(np.random.PCG64(77))
+    n_tok = t * h * w // 4
+    ids = torch.tensor([rng.integers(0, 151643, 12).tolist() + [151652] + [151655] * n_tok + [151653] +
+                        rng.integers(0, 151643, wl["S"] - 4 - n_tok - 2 - 12).tolist()])
+    g = torch.Generator(device="cpu").manual_seed(99)
+    px = torch.randn(t * h * w, 1176, generator=g).bfloat16().to(dev)
+    rgb = torch.rand(1, 2, 224, 224, 3, generator=g).bfloat16().to(dev)
+    dep = (torch.rand(1, 2, 224, 224, 1, generator=g) * 5).bfloat16().to(dev)
+    x0 = torch.randn(wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
+    nz = torch.randn(wl["K"] - 1, wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
+
+    def one_env():
+        with torch.no_grad():
+            lat = Q.generate_latents(sd2, cfg, ids, px, [list(wl["grid"])])
+            traj = O.predict_pointgoal_action_async(sd1, lat, rgb, dep, x0, nz, K=wl["K"])
+        return O.traj_to_actions(traj)
+
+    for _ in range(max(args.warmup, 2)):
+        one_env()
+    torch.cuda.synchronize()
+    n = max(args.steps, 3)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        one_env()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    out = {"metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": 1.0 / dt, "unit": "policy-steps/s",
+           "impl": "eager_gpu", "n_gpus": 1, "steps": n, "warmup": max(args.warmup, 2), "ms_per_step": dt * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": args.workload, "batch": 1,
+                      "note": "reference algorithm as eager PyTorch on the GPU (oracle restatement, bf16, explicit softmax "
+                              "attention), one environment per call like the reference; wall clock incl. the action tail"}}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--workload", default="dual_system", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.impl == "eager":
+        run_eager_gpu(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         run_ours(args, wl)
