@@ -203,8 +203,9 @@ def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, e
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, budget_s=20.0)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -520,7 +521,7 @@ def run_reference(args, wl):
                       "note": "reference algorithm on host cores (CPU oracle port; /root/reference is Python and cannot travel)"},
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "policy-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_eager_gpu(args, wl):
@@ -570,7 +571,25 @@ def run_eager_gpu(args, wl):
            "config": {"workload": args.workload, "batch": 1,
                       "note": "reference algorithm as eager PyTorch on the GPU (oracle restatement, bf16, explicit softmax "
                               "attention), one environment per call like the reference; wall clock incl. the action tail"}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_OUT_FD = 1
+
+
+def _claim_stdout():
+    """Keep stdout for the JSON line alone: library chatter written to fd 1 (e.g. NCCL's version banner) goes to stderr."""
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(out):
+    """The ONE JSON line, written straight to fd 1: a rank process that leaves through NCCL/CUDA teardown without running
+    Python's stdio finalisation (seen under torchrun with stdout redirected to a file) must not lose it."""
+    sys.stdout.flush()
+    os.write(_OUT_FD, (json.dumps(out) + "\n").encode())
 
 
 def main():
@@ -582,6 +601,7 @@ def main():
     ap.add_argument("--workload", default="dual_system", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == "eager":
         run_eager_gpu(args, wl)
@@ -592,4 +612,14 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        if not isinstance(sys.exc_info()[1], SystemExit):
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
+        raise
+    sys.stdout.flush()
+    sys.stderr.flush()
