@@ -149,6 +149,28 @@ int n1_qwen_vit(n1_handle h, n1_vit_plan p, void* ws, size_t ws_bytes, const voi
 int n1_llm_prefill(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* image_feats_bf16,
                    void* latents_bf16, void* stream);
 
+/* ---- greedy decode of System 2 with KV reuse into the latent plan
+ * replaces: self.model.generate(**inputs, max_new_tokens=128, do_sample=False, use_cache=True)
+ *                                                          (internvla_n1_policy.py L169-176; habitat_vln_evaluator.py L418-448)
+ *           followed by self.model.generate_latents(output_ids, pixel_values, image_grid_thw)   (policy L187-190),
+ *           which in the reference repeats the vision tower and the whole prefill; here the K/V cache of the decode is
+ *           extended by [last token, TRAJ x n_query] instead.
+ * A generation plan is an n1_llm_plan created over the prompts alone (no TRAJ tokens) with cache slots for
+ * max_new_tokens + n_query more rows per sequence; n1_llm_prefill refuses it and n1_llm_generate refuses latent plans.
+ * The state_dict given to n1_s2_load must hold "lm_head.weight" (n1_s2_has_lm_head). */
+int n1_gen_plan_create(n1_handle h, const int32_t* input_ids_host, const int32_t* lens_host, int B,
+                       const int32_t* grid_thw_host, int n_img, int max_new_tokens, n1_llm_plan* out, void* stream);
+size_t n1_generate_workspace_bytes(n1_handle h, n1_llm_plan p);
+int n1_s2_has_lm_head(n1_handle h);
+/* image_feats bf16 [n_image_tokens, 3584] (n1_qwen_vit output).  eos_ids_host: <= 4 ids (Qwen2.5-VL generation
+ * config: 151645, 151643); a sequence stops after emitting one of them (the id is part of its output) or after
+ * max_new_tokens.  tokens_host [B, max_new_tokens] int32 (tail filled with pad_id), lens_host [B] = tokens emitted.
+ * latents_bf16 (device, [B, n_query, 3584]) may be NULL.  *passes_host (nullable) = decode passes run.  The call
+ * synchronises `stream` (the stop test reads a device counter after every token). */
+int n1_llm_generate(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* image_feats_bf16,
+                    const int32_t* eos_ids_host, int n_eos, int32_t pad_id, int32_t* tokens_host, int32_t* lens_host,
+                    void* latents_bf16, int32_t* passes_host, void* stream);
+
 /* HOST-only integer helpers (no GPU needed): the same planners, exposed for bit-exact parity tests. */
 int n1_rope_index(const int32_t* input_ids_host, int len, const int32_t* grid_thw_host, int n_img, int merge,
                   int32_t* pos3_host /* [3, len] */, int32_t* delta_host);

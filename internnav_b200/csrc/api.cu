@@ -281,6 +281,44 @@ int n1_llm_prefill(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const 
   });
 }
 
+int n1_gen_plan_create(n1_handle h, const int32_t* ids, const int32_t* lens, int B, const int32_t* grid, int n_img,
+                       int max_new_tokens, n1_llm_plan* out, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!ids || !lens || B <= 0 || !out || max_new_tokens < 1) throw Error(N1_ERR_ARG, "n1_gen_plan_create: bad arguments");
+    n1_llm_plan_s* w = new n1_llm_plan_s();
+    try {
+      w->p = h->s2.make_llm_plan(ids, lens, B, grid, n_img, S(stream), max_new_tokens);
+    } catch (...) {
+      delete w;
+      throw;
+    }
+    *out = w;
+  });
+}
+size_t n1_generate_workspace_bytes(n1_handle h, n1_llm_plan p) {
+  size_t r = 0;
+  guard([&] {
+    if (!h || !p) throw Error(N1_ERR_ARG, "null handle/plan");
+    r = h->s2.ws_generate(*p->p);
+  });
+  return r;
+}
+int n1_s2_has_lm_head(n1_handle h) { return h && h->s2.has_lm_head() ? 1 : 0; }
+int n1_llm_generate(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* image_feats,
+                    const int32_t* eos, int n_eos, int32_t pad_id, int32_t* tokens, int32_t* lens, void* latents,
+                    int32_t* passes, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    if (n_eos < 0 || n_eos > 4 || (n_eos > 0 && !eos)) throw Error(N1_ERR_ARG, "n1_llm_generate: 0..4 eos ids");
+    GenResult r;
+    r.tokens = tokens, r.lens = lens;
+    h->s2.llm_generate(*p->p, ws, ws_bytes, B16(image_feats), eos, n_eos, pad_id, r, B16(latents), S(stream));
+    if (passes) *passes = r.steps;
+  });
+}
+
 int n1_rope_index(const int32_t* ids, int len, const int32_t* grid, int n_img, int merge, int32_t* pos3,
                   int32_t* delta) {
   return guard([&] {

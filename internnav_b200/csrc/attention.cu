@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
   const int q0 = qt * BQ;
   if (q0 >= sq) return;
   const int kb = b / p.kv_div;
-  const int k_start = p.cu_k ? p.cu_k[kb] : kb * p.seq_k;
-  const int sk = p.cu_k ? p.cu_k[kb + 1] - k_start : p.seq_k;
+  const int k_start = p.k_len ? kb * p.k_slot : (p.cu_k ? p.cu_k[kb] : kb * p.seq_k);
+  const int sk = p.k_len ? p.k_len[kb] : (p.cu_k ? p.cu_k[kb + 1] - k_start : p.seq_k);
   const int hk = h / (p.heads_q / p.heads_kv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -409,7 +409,7 @@ void attention(const AttnParams& p, cudaStream_t stream) {
   N1_CHECK(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "attention: misaligned strides");
   N1_CHECK(!p.cu_q || p.max_seq_q > 0, "attention: varlen needs max_seq_q");
   N1_CHECK(p.batch <= 65535 && p.heads_q <= 65535, "attention: grid too large");
-  if (p.hd == 48 && !p.cu_q && !p.cu_k && p.heads_q == p.heads_kv && p.heads_q <= 8 && p.seq_q <= 32 && p.seq_k <= 64 &&
+  if (p.hd == 48 && !p.cu_q && !p.cu_k && !p.k_len && p.heads_q == p.heads_kv && p.heads_q <= 8 && p.seq_q <= 32 && p.seq_k <= 64 &&
       p.ldo % 8 == 0) {
     const int nkp = (p.seq_k + 15) / 16;
     if (nkp == 1) launch_attn_small<1>(p, stream);

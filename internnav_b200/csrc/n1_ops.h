@@ -99,6 +99,8 @@ struct AttnParams {
   int causal;            // bottom-right aligned causal mask (key j visible to query i iff j <= i + seq_k - seq_q)
   float scale;
   int max_seq_q;         // upper bound on query length (grid sizing) when varlen
+  const int* k_len;      // optional [batch_kv] device: slotted K/V (a KV cache) -- sequence kb occupies rows
+  int k_slot;            //   [kb * k_slot, kb * k_slot + k_len[kb]); overrides cu_k / seq_k
 };
 void attention(const AttnParams& p, cudaStream_t stream);
 

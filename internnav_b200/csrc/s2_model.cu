@@ -86,7 +86,10 @@ Lin plain_lin(Arena& a, const WeightSource& ws, const std::string& name, bool bi
 VitPlan::~VitPlan() {
   cudaFree(window_index), cudaFree(reverse_index), cudaFree(cu_window), cudaFree(cu_full), cudaFree(rope);
 }
-LlmPlan::~LlmPlan() { cudaFree(cu), cudaFree(kind), cudaFree(src), cudaFree(out_rows), cudaFree(rope); }
+LlmPlan::~LlmPlan() {
+  cudaFree(cu), cudaFree(kind), cudaFree(src), cudaFree(out_rows), cudaFree(rope);
+  cudaFree(dest_rows), cudaFree(d_len), cudaFree(d_delta);
+}
 
 // ------------------------------------------------------------------------------------------------ load
 void S2Model::load(const WeightSource& ws, const S2Dims& d, cudaStream_t s) {
@@ -139,6 +142,8 @@ void S2Model::load(const WeightSource& ws, const S2Dims& d, cudaStream_t s) {
     b.down = plain_lin(arena_, m, p + "mlp.down_proj", false, H, d.inter, s);
   }
   final_norm_ = m.f32(arena_, "norm.weight", s);
+  // Qwen2.5-VL-7B does not tie the output projection to the embedding; generate_latents never reads it, generate() does.
+  if (ws.has("lm_head.weight")) lm_head_ = plain_lin(arena_, ws, "lm_head", false, d.vocab, H, s);
   N1_CUDA(cudaStreamSynchronize(s));
   loaded_ = true;
 }
@@ -164,11 +169,13 @@ VitPlan* S2Model::make_vit_plan(const int32_t* grid, int n_img, cudaStream_t s) 
 }
 
 LlmPlan* S2Model::make_llm_plan(const int32_t* ids, const int32_t* lens, int B, const int32_t* grid, int n_img,
-                                cudaStream_t s) const {
+                                cudaStream_t s, int max_new_tokens) const {
   N1_CHECK(loaded_, "System-2 weights not loaded");
+  N1_CHECK(max_new_tokens != 0, "generation plan: max_new_tokens must be >= 1");
   std::unique_ptr<LlmPlan> p(new LlmPlan());
-  const int nq = dims.n_query, unit = dims.v_merge * dims.v_merge;
-  p->B = B, p->n_query = nq;
+  const bool gen = max_new_tokens > 0;
+  const int nq = gen ? 0 : dims.n_query, unit = dims.v_merge * dims.v_merge;
+  p->B = B, p->n_query = dims.n_query;
   std::vector<int> kind, src, out_rows, pos_all;
   p->h_cu.push_back(0);
   int cursor = 0;
@@ -176,6 +183,7 @@ LlmPlan* S2Model::make_llm_plan(const int32_t* ids, const int32_t* lens, int B, 
   std::vector<std::vector<int>> pos_seq(B);
   for (int b = 0; b < B; ++b) {
     const int len = lens[b];
+    N1_CHECK(len > 0, "empty prompt");
     std::vector<int> seq(ids + off, ids + off + len);
     off += len;
     for (int q = 0; q < nq; ++q) seq.push_back(kTrajTokenId);  // internvla_n1.py L327
@@ -194,11 +202,13 @@ LlmPlan* S2Model::make_llm_plan(const int32_t* ids, const int32_t* lens, int B, 
         kind.push_back(0), src.push_back(seq[i]);
       }
     }
+    if (gen) out_rows.push_back((int)kind.size() - 1);  // logits of the last prompt token start the decode
     p->h_cu.push_back(p->h_cu.back() + L);
     p->max_len = std::max(p->max_len, L);
   }
   p->tokens = p->h_cu.back();
   p->n_image_tokens = img_tok;
+  p->n_out = (int)out_rows.size();
   long expect = 0;
   for (int i = 0; i < cursor; ++i) expect += (long)grid[i * 3] * grid[i * 3 + 1] * grid[i * 3 + 2] / unit;
   N1_CHECK(expect == img_tok, "Image features and image tokens do not match: tokens " + std::to_string(img_tok) +
@@ -218,6 +228,18 @@ LlmPlan* S2Model::make_llm_plan(const int32_t* ids, const int32_t* lens, int B, 
   const int half = dims.head_dim / 2;
   N1_CUDA(cudaMalloc(&p->rope, (size_t)p->tokens * half * sizeof(float2)));
   mrope_table(pos, p->rope, p->tokens, half, dims.mrope[0], dims.mrope[1], dims.rope_theta, s);
+  if (gen) {
+    p->max_new = max_new_tokens;
+    p->slot = p->max_len + max_new_tokens + dims.n_query;
+    std::vector<int> dest(p->tokens), len_v(B);
+    for (int b = 0; b < B; ++b) {
+      len_v[b] = p->h_cu[b + 1] - p->h_cu[b];
+      for (int i = 0; i < len_v[b]; ++i) dest[p->h_cu[b] + i] = b * p->slot + i;
+    }
+    p->dest_rows = upload(dest, s);
+    p->d_len = upload(len_v, s);
+    p->d_delta = upload(p->h_delta, s);
+  }
   N1_CUDA(cudaStreamSynchronize(s));
   cudaFree(pos);
   return p.release();
@@ -282,12 +304,13 @@ void S2Model::vit_forward(const VitPlan& p, void* ws, size_t ws_bytes, const bf1
 }
 
 // ------------------------------------------------------------------------------------------------ decoder prefill
-size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf16* out, cudaStream_t s) const {
+size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf16* out, cudaStream_t s,
+                         const KvCache* kv) const {
   const int H = dims.hidden, hd = dims.head_dim;
   const long T = p.tokens;
   const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd;
   bf16* x = c.take<bf16>(T * H);
-  const long sel_rows = 3L * p.B * p.n_query;  // the last layer reuses `ln` for three [B * n_query, H] buffers
+  const long sel_rows = 3L * p.n_out;  // the last layer reuses `ln` for three [n_out, H] buffers
   bf16* ln = c.take<bf16>((T > sel_rows ? T : sel_rows) * H);
   bf16* qkv = c.take<bf16>(T * qkv_n);
   bf16* att = c.take<bf16>(T * H);
@@ -300,6 +323,9 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
     layernorm(x, H, ln, H, b.n1, nullptr, (int)T, H, dims.rms_eps, 1, s);
     linear(b.qkv, ln, H, qkv, qkv_n, (int)T, GemmEpilogue(), s);
     apply_rope(qkv, qkv_n, p.rope, T, dims.heads + dims.kv_heads, hd, s);
+    if (kv)  // keep the rotated keys and the values of every prompt token for the decode passes
+      kv_append(qkv, qkv_n, dims.heads * hd, (dims.heads + dims.kv_heads) * hd, dims.kv_heads * hd, p.dest_rows, T,
+                kv->k + l * kv->layer_stride, kv->v + l * kv->layer_stride, s);
     AttnParams a = {};
     a.q = qkv, a.k = qkv + (long)dims.heads * hd, a.v = qkv + (long)(dims.heads + dims.kv_heads) * hd, a.o = att;
     a.ldq = a.ldk = a.ldv = qkv_n, a.ldo = H;
@@ -312,7 +338,8 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
     if (l == dims.layers - 1) {
       // Only the n_query TRAJ rows of each sequence are read after the last layer (internvla_n1.py L345): every token
       // still contributes K/V to the attention above, but o_proj and the MLP run on those B * n_query rows alone.
-      const int R = p.B * p.n_query;
+      // (Generation plans read the last prompt row of each sequence instead.)
+      const int R = p.n_out;
       bf16* att_sel = ln;                      // [R, H] scratch (ln is free here)
       bf16* x_sel = ln + (long)R * H;          // [R, H]
       bf16* ln_sel = ln + 2L * R * H;          // [R, H]
@@ -344,8 +371,123 @@ size_t S2Model::ws_llm(const LlmPlan& p) const { return llm_impl(Carver(nullptr,
 void S2Model::llm_prefill(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, bf16* out,
                           cudaStream_t s) const {
   N1_CHECK(loaded_ && ws, "llm_prefill: not loaded / null workspace");
+  N1_CHECK(p.max_new == 0, "llm_prefill: this is a generation plan (use llm_generate)");
   if (ws_bytes < ws_llm(p)) throw Error(-7, "llm_prefill: workspace too small");
   llm_impl(Carver(ws, ws_bytes), p, image_feats, out, s);
+}
+
+// ------------------------------------------------------------------------------------------------ greedy decode
+struct S2Model::GenBufs {
+  int *cur_tok, *gen, *finished, *next, *k_len, *n_active, *out_tokens, *dest, *pos3, *kind, *src;
+  float2* rope;
+  bf16 *x, *ln, *qkv, *att, *hid, *normed, *logits;
+};
+
+// One pass of B * per_seq new tokens (rows of g.x) through all layers against the cache: per_seq = 1 is a decode step,
+// per_seq = 1 + n_query the latent pass.  g.dest / g.rope / g.k_len describe the chunk (gen_rows).  Result: final-norm
+// states of every row in g.normed.
+void S2Model::chunk_pass(const GenBufs& g, const LlmPlan& p, const KvCache& kv, int per_seq, cudaStream_t s) const {
+  const int H = dims.hidden, hd = dims.head_dim, R = p.B * per_seq;
+  const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd, kvd = dims.kv_heads * hd;
+  for (int l = 0; l < dims.layers; ++l) {
+    const LBlock& b = lblk_[l];
+    layernorm(g.x, H, g.ln, H, b.n1, nullptr, R, H, dims.rms_eps, 1, s);
+    linear(b.qkv, g.ln, H, g.qkv, qkv_n, R, GemmEpilogue(), s);
+    apply_rope(g.qkv, qkv_n, g.rope, R, dims.heads + dims.kv_heads, hd, s);
+    bf16* ck = kv.k + l * kv.layer_stride;
+    bf16* cv = kv.v + l * kv.layer_stride;
+    kv_append(g.qkv, qkv_n, dims.heads * hd, (dims.heads + dims.kv_heads) * hd, kvd, g.dest, R, ck, cv, s);
+    AttnParams a = {};
+    a.q = g.qkv, a.k = ck, a.v = cv, a.o = g.att;
+    a.ldq = qkv_n, a.ldk = a.ldv = kvd, a.ldo = H;
+    a.heads_q = dims.heads, a.heads_kv = dims.kv_heads, a.hd = hd;
+    a.batch = p.B, a.seq_q = per_seq, a.k_len = g.k_len, a.k_slot = p.slot;
+    a.kv_div = 1, a.causal = 1, a.scale = 1.0f / sqrtf((float)hd);
+    attention(a, s);
+    GemmEpilogue res;
+    res.residual = g.x, res.ldr = H;
+    linear(b.o, g.att, H, g.x, H, R, res, s);
+    layernorm(g.x, H, g.ln, H, b.n2, nullptr, R, H, dims.rms_eps, 1, s);
+    GemmEpilogue sw;
+    sw.act = ACT_SWIGLU;
+    linear(b.gateup, g.ln, H, g.hid, inter_pad_, R, sw, s);
+    linear(b.down, g.hid, inter_pad_, g.x, H, R, res, s);
+  }
+  layernorm(g.x, H, g.normed, H, final_norm_, nullptr, R, H, dims.rms_eps, 1, s);
+}
+
+size_t S2Model::gen_impl(Carver c, const LlmPlan& p, const bf16* image_feats, const int32_t* eos, int n_eos,
+                         int32_t pad, GenResult* out, bf16* latents, cudaStream_t s) const {
+  const int H = dims.hidden, hd = dims.head_dim, B = p.B, nq = dims.n_query;
+  const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd, kvd = dims.kv_heads * hd, half = hd / 2;
+  const int R5 = B * (nq + 1);
+  KvCache kv;
+  kv.layer_stride = (long)B * p.slot * kvd;
+  kv.k = c.take<bf16>((size_t)dims.layers * kv.layer_stride);
+  kv.v = c.take<bf16>((size_t)dims.layers * kv.layer_stride);
+  GenBufs g;
+  g.cur_tok = c.take<int>(B), g.gen = c.take<int>(B), g.finished = c.take<int>(B), g.next = c.take<int>(B);
+  g.k_len = c.take<int>(B), g.n_active = c.take<int>(1), g.out_tokens = c.take<int>((size_t)B * p.max_new);
+  g.dest = c.take<int>(R5), g.pos3 = c.take<int>(3 * R5), g.kind = c.take<int>(R5), g.src = c.take<int>(R5);
+  g.rope = c.take<float2>((size_t)R5 * half);
+  g.x = c.take<bf16>((size_t)R5 * H), g.ln = c.take<bf16>((size_t)R5 * H), g.qkv = c.take<bf16>((size_t)R5 * qkv_n);
+  g.att = c.take<bf16>((size_t)R5 * H), g.hid = c.take<bf16>((size_t)R5 * inter_pad_);
+  g.normed = c.take<bf16>((size_t)R5 * H), g.logits = c.take<bf16>((size_t)B * dims.vocab);
+  if (c.dry()) return llm_impl(c, p, nullptr, nullptr, nullptr, &kv);  // prefill scratch follows the decode state
+
+  // 1. prompt prefill, K/V kept; final-norm state of the last prompt token of each sequence -> g.normed [B, H]
+  llm_impl(c, p, image_feats, g.normed, s, &kv);
+  std::vector<int32_t> fill((size_t)B * p.max_new, pad);
+  N1_CUDA(cudaMemcpyAsync(g.out_tokens, fill.data(), fill.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  N1_CUDA(cudaMemsetAsync(g.gen, 0, B * sizeof(int), s));
+  N1_CUDA(cudaMemsetAsync(g.finished, 0, B * sizeof(int), s));
+  int steps = 0;
+  for (int it = 0; it < p.max_new; ++it) {
+    // logits = lm_head(hidden[:, -1]) in bf16, next = argmax (GenerationMixin greedy search)
+    linear(lm_head_, g.normed, H, g.logits, dims.vocab, B, GemmEpilogue(), s);
+    argmax_rows(g.logits, dims.vocab, dims.vocab, B, g.next, s);
+    gen_update(g.next, g.cur_tok, g.gen, g.finished, g.out_tokens, p.max_new, eos, n_eos, B, g.n_active, s);
+    int active = 0;
+    N1_CUDA(cudaMemcpyAsync(&active, g.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+    N1_CUDA(cudaStreamSynchronize(s));
+    if (active == 0) break;
+    // 2. one decode pass: the token just sampled is row (len + gen - 1) of its sequence
+    gen_rows(p.d_len, p.d_delta, g.gen, 1, 1, B, p.slot, g.dest, g.pos3, g.k_len, s);
+    mrope_table(g.pos3, g.rope, B, half, dims.mrope[0], dims.mrope[1], dims.rope_theta, s);
+    gather_rows(embed_, g.cur_tok, g.x, B, 1, H, s);
+    chunk_pass(g, p, kv, 1, s);
+    ++steps;
+  }
+  if (latents) {
+    // 3. generate_latents(output_ids, ...) on the cache: the last sampled token has no K/V yet, so the pass covers
+    //    [last token, TRAJ x nq]; rows 1..nq of each sequence are the latent plan (internvla_n1.py L327, L345).
+    gen_rows(p.d_len, p.d_delta, g.gen, 1, nq + 1, B, p.slot, g.dest, g.pos3, g.k_len, s);
+    mrope_table(g.pos3, g.rope, R5, half, dims.mrope[0], dims.mrope[1], dims.rope_theta, s);
+    latent_src(g.cur_tok, B, nq, g.kind, g.src, s);
+    build_embeds(g.kind, g.src, embed_, nullptr, latentq_, g.x, R5, H, s);
+    chunk_pass(g, p, kv, nq + 1, s);
+    N1_CUDA(cudaMemcpy2DAsync(latents, (size_t)nq * H * sizeof(bf16), g.normed + H, (size_t)(nq + 1) * H * sizeof(bf16),
+                              (size_t)nq * H * sizeof(bf16), B, cudaMemcpyDeviceToDevice, s));
+  }
+  N1_CUDA(cudaMemcpyAsync(out->tokens, g.out_tokens, (size_t)B * p.max_new * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  N1_CUDA(cudaMemcpyAsync(out->lens, g.gen, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  N1_CUDA(cudaStreamSynchronize(s));
+  out->steps = steps;
+  return c.used();
+}
+
+size_t S2Model::ws_generate(const LlmPlan& p) const {
+  N1_CHECK(p.max_new > 0, "ws_generate: not a generation plan");
+  return gen_impl(Carver(nullptr, 0), p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr);
+}
+void S2Model::llm_generate(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, const int32_t* eos,
+                           int n_eos, int32_t pad, GenResult& out, bf16* latents, cudaStream_t s) const {
+  N1_CHECK(loaded_ && ws, "llm_generate: not loaded / null workspace");
+  N1_CHECK(p.max_new > 0, "llm_generate: the plan was not created for generation");
+  if (!has_lm_head()) throw Error(-6, "llm_generate: lm_head.weight was not part of the loaded state_dict");
+  N1_CHECK(out.tokens && out.lens, "llm_generate: null output buffers");
+  if (ws_bytes < ws_generate(p)) throw Error(-7, "llm_generate: workspace too small");
+  gen_impl(Carver(ws, ws_bytes), p, image_feats, eos, n_eos, pad, &out, latents, s);
 }
 
 }  // namespace n1

@@ -34,11 +34,22 @@ struct VitPlan {
 // Device-resident token bookkeeping for one batch of prompts (generate_latents appends n_query TRAJ tokens each).
 struct LlmPlan {
   int B = 0, max_len = 0, n_query = 0;
+  int n_out = 0;  // rows read after the last layer: B * n_query TRAJ rows (latent plan) or the B last prompt rows
   long tokens = 0, n_image_tokens = 0;
   std::vector<int> h_cu, h_pos3, h_delta;
   int *cu = nullptr, *kind = nullptr, *src = nullptr, *out_rows = nullptr;
   float2* rope = nullptr;  // [tokens, head_dim / 2]
+  // generation plans only (max_new > 0): every sequence owns `slot` rows of the per-layer K/V cache
+  int max_new = 0, slot = 0;
+  int *dest_rows = nullptr, *d_len = nullptr, *d_delta = nullptr;  // [tokens], [B], [B]
   ~LlmPlan();
+};
+
+// Result of one greedy generation (host side of n1_llm_generate).
+struct GenResult {
+  int32_t* tokens = nullptr;  // host [B, max_new], unfilled entries = pad
+  int32_t* lens = nullptr;    // host [B]
+  int steps = 0;              // decode passes executed after the prefill
 };
 
 class S2Model {
@@ -49,8 +60,10 @@ class S2Model {
 
   VitPlan* make_vit_plan(const int32_t* grid_thw_host, int n_img, cudaStream_t s) const;
   // ids: packed prompt token ids (host), lens[B]; TRAJ tokens are appended per sequence by the planner.
+  // max_new_tokens < 0: latent plan (generate_latents).  >= 1: generation plan (no TRAJ tokens; KV-cache slots sized
+  // for the prompt + max_new_tokens + n_query rows).
   LlmPlan* make_llm_plan(const int32_t* ids_host, const int32_t* lens_host, int B, const int32_t* grid_thw_host,
-                         int n_img, cudaStream_t s) const;
+                         int n_img, cudaStream_t s, int max_new_tokens = -1) const;
 
   size_t ws_vit(const VitPlan& p) const;
   // pixels bf16 [n_patches, 3 * tpatch * patch^2] -> out bf16 [n_patches / merge^2, v_out] (original token order)
@@ -59,8 +72,21 @@ class S2Model {
   // image_feats bf16 [n_image_tokens, hidden] -> out bf16 [B, n_query, hidden] (final-norm states of the TRAJ rows)
   void llm_prefill(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, bf16* out,
                    cudaStream_t s) const;
+  // Greedy decode (model.generate(do_sample=False), internvla_n1_policy.py L169-176) on a generation plan: prefill with
+  // K/V kept per layer, then one token per pass until every sequence emitted an eos id or max_new tokens.  When
+  // `latents` is non-null the cache is reused for generate_latents(output_ids, ...) (internvla_n1.py L320-347): one more
+  // pass over [last token, TRAJ x n_query] per sequence -> latents bf16 [B, n_query, hidden].  Synchronises `s`.
+  size_t ws_generate(const LlmPlan& p) const;
+  void llm_generate(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, const int32_t* eos, int n_eos,
+                    int32_t pad, GenResult& out, bf16* latents, cudaStream_t s) const;
+  bool has_lm_head() const { return lm_head_.w != nullptr; }
 
  private:
+  struct KvCache {
+    bf16 *k = nullptr, *v = nullptr;  // [layers][B * slot][kv_heads * head_dim]
+    long layer_stride = 0;
+  };
+  struct GenBufs;
   struct VBlock {
     float *n1 = nullptr, *n2 = nullptr;
     Lin qkv, proj, gateup, down;
@@ -70,7 +96,11 @@ class S2Model {
     Lin qkv, o, gateup, down;
   };
   size_t vit_impl(Carver c, const VitPlan& p, const bf16* pixels, bf16* out, cudaStream_t s) const;
-  size_t llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf16* out, cudaStream_t s) const;
+  size_t llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf16* out, cudaStream_t s,
+                  const KvCache* kv = nullptr) const;
+  size_t gen_impl(Carver c, const LlmPlan& p, const bf16* image_feats, const int32_t* eos, int n_eos, int32_t pad,
+                  GenResult* out, bf16* latents, cudaStream_t s) const;
+  void chunk_pass(const GenBufs& g, const LlmPlan& p, const KvCache& kv, int per_seq, cudaStream_t s) const;
 
   Arena arena_;
   bool loaded_ = false;
@@ -83,6 +113,7 @@ class S2Model {
   bf16* latentq_ = nullptr;  // [n_query, hidden]
   std::vector<LBlock> lblk_;
   float* final_norm_ = nullptr;
+  Lin lm_head_;  // optional ("lm_head.weight"); only generate() needs it
 };
 
 }  // namespace n1

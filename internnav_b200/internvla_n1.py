@@ -6,8 +6,12 @@ image_grid_thw)`, `generate_traj(traj_latents, images_dp, depths_dp, ...)`, attr
 `.config.{system1, n_query}`, `.get_model()`, `.device`.  Both systems execute in libn1b200.so; PyTorch carries the
 tensors.  Everything is batched over B independent environments, each treated exactly like the reference's single one.
 
-Not built yet: the greedy decode loop `generate()`, the NextDiT System-1 branch, and the training
-`forward` -- calling them raises NotImplementedError rather than falling back to anything slower.
+`generate()` is the greedy decode of System 2 (`model.generate(do_sample=False)`, internvla_n1_policy.py L169-176) on a
+KV cache; `generate_with_latents()` additionally extends that cache by the TRAJ tokens, which replaces the reference's
+second full prefill in `generate_latents(output_ids, ...)` (policy L187-190).
+
+Not built yet: the NextDiT System-1 branch and the training `forward` -- calling them raises
+NotImplementedError rather than falling back to anything slower.
 """
 from types import SimpleNamespace
 
@@ -16,7 +20,7 @@ import torch
 
 from .navdp import NavDP_Policy_DPT_CriticSum_DAT
 from .postprocess import batched_traj_to_actions, s1_action_list
-from .qwen import QWEN25VL_7B, System2
+from .qwen import EOS_TOKEN_IDS, PAD_TOKEN_ID, QWEN25VL_7B, System2
 
 TRAJ_TOKEN_INDEX = 151667
 IMAGE_TOKEN_INDEX = 151655
@@ -130,9 +134,38 @@ class InternVLAN1ForCausalLM:
         mask = loss_mask.flatten(0, 1)[:, None, None].to(err.device)
         return (err * mask).sum() / mask.sum() / (err.shape[1] * err.shape[2])
 
-    def generate(self, *a, **k):
-        raise NotImplementedError("greedy decode (model.generate) is not part of the n1b200 hot path yet (SURVEY.md §8f "
-                                  "rank 2); there is no fallback implementation")
+    def generate(self, input_ids=None, pixel_values=None, image_grid_thw=None, max_new_tokens=128, do_sample=False,
+                 eos_token_id=None, pad_token_id=None, return_dict_in_generate=False, with_latents=False, **hf_kwargs):
+        """`model.generate(**inputs, max_new_tokens=128, do_sample=False, use_cache=True, past_key_values=None,
+        return_dict_in_generate=True).sequences` (internvla_n1_policy.py L169-176) for B prompts.  `sequences` is
+        [B, S_max + longest generation] int64: prompt, generated ids (the eos id included), then `pad_token_id`; ragged
+        prompts are right-aligned the way the HF processor pads them (left padding).  Other HF keyword arguments
+        (attention_mask, use_cache, past_key_values, ...) are accepted and have no effect on greedy search."""
+        if do_sample or hf_kwargs.get("num_beams", 1) != 1:
+            raise NotImplementedError("n1b200 implements greedy search only (the reference calls do_sample=False)")
+        eos = EOS_TOKEN_IDS if eos_token_id is None else \
+            (tuple(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else (int(eos_token_id),))
+        pad = PAD_TOKEN_ID if pad_token_id is None else int(pad_token_id)
+        prompts = self._prompts(input_ids)
+        grid = image_grid_thw.tolist() if torch.is_tensor(image_grid_thw) else image_grid_thw
+        with torch.no_grad():
+            toks, lat, passes = self._s2.generate(prompts, pixel_values, grid, max_new_tokens=int(max_new_tokens),
+                                                  eos_token_ids=eos, pad_token_id=pad, with_latents=with_latents)
+        s_max = max(len(p) for p in prompts)
+        g_max = max(len(t) for t in toks)
+        seq = torch.full((len(prompts), s_max + g_max), pad, dtype=torch.int64)
+        for b, (p, t) in enumerate(zip(prompts, toks)):
+            seq[b, s_max - len(p):s_max] = torch.tensor(p, dtype=torch.int64)
+            seq[b, s_max:s_max + len(t)] = torch.tensor(t, dtype=torch.int64)
+        out = SimpleNamespace(sequences=seq.to(self.device), generated=toks, latents=lat, decode_passes=passes)
+        return out if (return_dict_in_generate or with_latents) else out.sequences
+
+    def generate_with_latents(self, input_ids, pixel_values, image_grid_thw, max_new_tokens=128, **kw):
+        """One System-2 call of the dual-system policy (internvla_n1_policy.py L166-195): greedy answer tokens AND the
+        latent plan `generate_latents(output_ids, pixel_values, image_grid_thw)`, sharing one vision pass, one prefill
+        and the decode's K/V cache.  -> namespace(sequences, generated, latents [B, n_query, hidden], decode_passes)."""
+        return self.generate(input_ids, pixel_values, image_grid_thw, max_new_tokens=max_new_tokens, with_latents=True,
+                             return_dict_in_generate=True, **kw)
 
     def forward(self, *a, **k):
         raise NotImplementedError("the full training forward/backward (SURVEY.md §8 row a13) is not built: the System-1 "

@@ -92,9 +92,10 @@ def random_navdp_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
 
 
 # ---------------------------------------------------------------------------------------------- System 2
-def s2_shapes(cfg):
+def s2_shapes(cfg, lm_head=False):
     """Qwen2.5-VL parameter names/shapes in the transformers==4.51 checkpoint layout the reference loads, plus
-    InternVLA-N1's `model.latent_queries` (internvla_n1_arch.py L123)."""
+    InternVLA-N1's `model.latent_queries` (internvla_n1_arch.py L123).  `lm_head=True` adds the untied output projection
+    that only the greedy decode reads."""
     Hv, H = cfg["v_hidden"], cfg["hidden"]
     unit = cfg["v_merge"] ** 2
     out = [("visual.patch_embed.proj.weight", (Hv, 3, cfg["v_tpatch"], cfg["v_patch"], cfg["v_patch"]))]
@@ -119,15 +120,17 @@ def s2_shapes(cfg):
                 (b + "self_attn.o_proj.weight", (H, qd)), (b + "mlp.gate_proj.weight", (cfg["inter"], H)),
                 (b + "mlp.up_proj.weight", (cfg["inter"], H)), (b + "mlp.down_proj.weight", (H, cfg["inter"]))]
     out += [("model.norm.weight", (H,))]
+    if lm_head:
+        out += [("lm_head.weight", (cfg["vocab"], H))]
     return OrderedDict(out)
 
 
-def random_s2_state_dict(cfg, seed=0, device="cuda", dtype=torch.bfloat16):
+def random_s2_state_dict(cfg, seed=0, device="cuda", dtype=torch.bfloat16, lm_head=False):
     """Random Qwen2.5-VL-shaped weights generated directly on `device` (synthetic benchmark runs; no checkpoints are
     available offline).  Norm weights ~1, matrices ~N(0, 1/fan_in), embeddings ~N(0, 1)."""
     g = torch.Generator(device=device).manual_seed(seed)
     out = OrderedDict()
-    for name, shape in s2_shapes(cfg).items():
+    for name, shape in s2_shapes(cfg, lm_head=lm_head).items():
         if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight") \
                 or name.endswith("norm.weight") or name.endswith("ln_q.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)

@@ -74,27 +74,42 @@ def _bind(L):
     L.n1_llm_prefill.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, vp, vp]
     L.n1_rope_index.restype = ctypes.c_int
     L.n1_vit_window_index.restype = ctypes.c_int
+    L.n1_gen_plan_create.restype = ctypes.c_int
+    L.n1_gen_plan_create.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), vp]
+    L.n1_generate_workspace_bytes.restype = ctypes.c_size_t
+    L.n1_generate_workspace_bytes.argtypes = [vp, vp]
+    L.n1_s2_has_lm_head.restype = ctypes.c_int
+    L.n1_s2_has_lm_head.argtypes = [vp]
+    L.n1_llm_generate.restype = ctypes.c_int
+    L.n1_llm_generate.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
+                                  ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp,
+                                  ctypes.POINTER(ctypes.c_int32), vp]
     L._s2_bound = True
 
 
 S2_SYMBOLS = ["n1_s2_load", "n1_vit_plan_create", "n1_vit_plan_destroy", "n1_vit_plan_patches", "n1_llm_plan_create",
               "n1_llm_plan_destroy", "n1_llm_plan_tokens", "n1_llm_plan_image_tokens", "n1_llm_plan_positions",
               "n1_vit_workspace_bytes", "n1_llm_workspace_bytes", "n1_qwen_vit", "n1_llm_prefill", "n1_rope_index",
-              "n1_vit_window_index"]
+              "n1_vit_window_index", "n1_gen_plan_create", "n1_generate_workspace_bytes", "n1_s2_has_lm_head",
+              "n1_llm_generate"]
+
+EOS_TOKEN_IDS = (151645, 151643)  # Qwen2.5-VL generation_config.json: <|im_end|>, <|endoftext|>
+PAD_TOKEN_ID = 151643
 
 
 def normalise_keys(state_dict):
     """Accept the transformers 4.51 layout (`visual.*`, `model.*`) and the 5.x one (`model.visual.*`,
-    `model.language_model.*`); System-1 keys (`model.navdp.*`) and `lm_head` are dropped."""
+    `model.language_model.*`); System-1 keys (`model.navdp.*`) are dropped, `lm_head.weight` is kept for generate()."""
     out = {}
     for k, v in state_dict.items():
         if k.startswith("model.visual."):
             k = k[len("model."):]
         elif k.startswith("model.language_model."):
             k = "model." + k[len("model.language_model."):]
-        if k.startswith("model.navdp.") or k.startswith("lm_head"):
+        if k.startswith("model.navdp."):
             continue
-        if k.startswith("visual.") or k.startswith("model."):
+        if k.startswith("visual.") or k.startswith("model.") or k == "lm_head.weight":
             out[k] = v
     return out
 
@@ -234,3 +249,51 @@ class System2:
     def generate_latents(self, prompts, pixel_values, grid_thw):
         """Batched InternVLAN1ForCausalLM.generate_latents: one prompt per environment, images in prompt order."""
         return self.prefill_latents(prompts, self.visual(pixel_values, grid_thw), grid_thw)
+
+    def gen_plan(self, prompts, grid_thw, max_new_tokens):
+        gkey = tuple(int(v) for g in grid_thw for v in g)
+        key = ("gen", int(max_new_tokens), tuple(tuple(p) for p in prompts), gkey)
+        hit = self._llm_plans.get(key)
+        if hit is None:
+            L = _lib.lib()
+            flat = [int(t) for p in prompts for t in p]
+            ids = (ctypes.c_int32 * len(flat))(*flat)
+            lens = (ctypes.c_int32 * len(prompts))(*[len(p) for p in prompts])
+            garr = (ctypes.c_int32 * max(1, len(gkey)))(*gkey)
+            p = c_void_p()
+            with torch.cuda.device(self.device):
+                check(L.n1_gen_plan_create(self._h(), ids, lens, len(prompts), garr, len(gkey) // 3, int(max_new_tokens),
+                                           ctypes.byref(p), _lib.stream_ptr()))
+            if len(self._llm_plans) > 64:
+                _, (old, _) = self._llm_plans.popitem()
+                L.n1_llm_plan_destroy(old)
+            hit = (p, len(prompts))
+            self._llm_plans[key] = hit
+        return hit[0]
+
+    def generate(self, prompts, pixel_values, grid_thw, max_new_tokens=128, eos_token_ids=EOS_TOKEN_IDS,
+                 pad_token_id=PAD_TOKEN_ID, with_latents=False, image_feats=None):
+        """Greedy decode for B prompts (`model.generate(do_sample=False, max_new_tokens=...)`, internvla_n1_policy.py
+        L169-176).  Returns (list of B generated-token lists, each ending with its eos id unless the budget ran out,
+        latents [B, n_query, hidden] or None, decode passes run).  With `with_latents` the K/V cache of the decode is
+        extended by the TRAJ tokens, which equals `generate_latents(output_ids, ...)` without a second prefill."""
+        L = _lib.lib()
+        if not L.n1_s2_has_lm_head(self._h()):
+            raise RuntimeError("generate() needs lm_head.weight in the loaded state_dict; there is no fallback")
+        plan = self.gen_plan(prompts, grid_thw, max_new_tokens)
+        B = len(prompts)
+        feats = self.visual(pixel_values, grid_thw) if image_feats is None else image_feats
+        feats = feats.to(self.device, torch.bfloat16).contiguous()
+        assert feats.shape[0] == L.n1_llm_plan_image_tokens(plan), "image features and image tokens do not match"
+        lat = torch.empty(B, self.cfg["n_query"], self.cfg["hidden"], device=self.device, dtype=torch.bfloat16) \
+            if with_latents else None
+        nb = L.n1_generate_workspace_bytes(self._h(), plan)
+        ws = self._scratch("gen", nb)
+        eos = (ctypes.c_int32 * max(1, len(eos_token_ids)))(*[int(e) for e in eos_token_ids])
+        toks = (ctypes.c_int32 * (B * int(max_new_tokens)))()
+        lens = (ctypes.c_int32 * B)()
+        passes = ctypes.c_int32(0)
+        check(L.n1_llm_generate(self._h(), plan, _lib.ptr(ws), nb, _lib.ptr(feats), eos, len(eos_token_ids),
+                                int(pad_token_id), toks, lens, _lib.ptr(lat), ctypes.byref(passes), _lib.stream_ptr()))
+        out = [list(toks[b * max_new_tokens: b * max_new_tokens + lens[b]]) for b in range(B)]
+        return out, lat, passes.value

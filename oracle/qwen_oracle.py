@@ -211,8 +211,41 @@ def generate_latents(sd, cfg, input_ids, pixel_values, image_grid_thw):
     return hs[:, -nq:, :]
 
 
+def next_token_logits(sd, cfg, input_ids, image_feats, image_grid_thw):
+    """Logits of the token after `input_ids` [1,S]: Qwen2_5_VLForConditionalGeneration.forward without a cache (embed,
+    splice image features, get_rope_index, decoder, lm_head on the last position).  Returns fp32 [vocab]."""
+    emb = sd["model.embed_tokens.weight"]
+    dt = image_feats.dtype
+    text = emb[input_ids.to(emb.device)].to(dt)
+    image_idx = input_ids == IMAGE_TOKEN_INDEX
+    text[image_idx.to(text.device)] = image_feats[: int(image_idx.sum())]
+    pos, _ = rope_index(input_ids, image_grid_thw, cfg["v_merge"])
+    hs = text_forward(sd, cfg, text, pos.to(text.device))
+    return F.linear(hs[0, -1], sd["lm_head.weight"].to(dt)).float()
+
+
+def greedy_generate(sd, cfg, input_ids, pixel_values, image_grid_thw, max_new_tokens=128, eos_token_ids=(151645, 151643),
+                    return_logits=False):
+    """`model.generate(**inputs, max_new_tokens=..., do_sample=False)` for one prompt (internvla_n1_policy.py L169-176):
+    GenerationMixin greedy search -- next = argmax(logits[:, -1]); the eos id is appended, then generation stops.  No KV
+    cache here: every step re-runs the full sequence, which is the same function of the same inputs.  Returns the list
+    of generated ids (and, optionally, the fp32 logits each one was chosen from)."""
+    feats = vit_forward(sd, cfg, pixel_values, image_grid_thw)
+    ids = input_ids.clone()
+    out, logs = [], []
+    for _ in range(max_new_tokens):
+        lg = next_token_logits(sd, cfg, ids, feats, image_grid_thw)
+        tok = int(torch.argmax(lg))
+        out.append(tok)
+        logs.append(lg)
+        ids = torch.cat([ids, torch.tensor([[tok]], dtype=ids.dtype)], dim=1)
+        if tok in eos_token_ids:
+            break
+    return (out, logs) if return_logits else out
+
+
 # ------------------------------------------------------------------------------------------------ synthetic weights
-def s2_shapes(cfg):
+def s2_shapes(cfg, lm_head=False):
     Hv, H = cfg["v_hidden"], cfg["hidden"]
     unit = cfg["v_merge"] ** 2
     out = [("visual.patch_embed.proj.weight", (Hv, 3, cfg["v_tpatch"], cfg["v_patch"], cfg["v_patch"]))]
@@ -237,15 +270,17 @@ def s2_shapes(cfg):
                 (b + "self_attn.o_proj.weight", (H, qd)), (b + "mlp.gate_proj.weight", (cfg["inter"], H)),
                 (b + "mlp.up_proj.weight", (cfg["inter"], H)), (b + "mlp.down_proj.weight", (H, cfg["inter"]))]
     out += [("model.norm.weight", (H,))]
+    if lm_head:
+        out += [("lm_head.weight", (cfg["vocab"], H))]
     return out
 
 
-def make_s2_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, vocab_rows=None):
+def make_s2_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, vocab_rows=None, lm_head=False):
     """Seeded synthetic weights (numpy PCG64, reproducible across machines).  `vocab_rows` truncates the random part of
     the embedding table for big configs (rows beyond it repeat) to keep generation fast."""
     import zlib
     sd = {}
-    for name, shape in s2_shapes(cfg):
+    for name, shape in s2_shapes(cfg, lm_head=lm_head):
         rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
         if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("layernorm.weight") \
                 or name.endswith("norm.weight") or name.endswith("ln_q.weight"):

@@ -17,7 +17,8 @@ import torch
 from oracle import qwen_oracle as Q
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLD = os.path.join(ROOT, "tests", "golden", "rope_index.json")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLD = os.path.join(GOLDEN, "rope_index.json")
 
 
 def _cases():
@@ -142,3 +143,78 @@ def test_decoder_vs_transformers():
         ref = m(inputs_embeds=emb, position_ids=pos).last_hidden_state
         mine = Q.text_forward(sd, cfg, emb, pos)
     assert torch.allclose(ref, mine, atol=3e-4, rtol=1e-4), (ref - mine).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ greedy decode
+GEN_CASE = dict(seed=5, prompt_seed=3, grids=[(1, 8, 12)], n_pre=6, n_post=10, pixel_seed=0, max_new=12)
+
+
+def _gen_case():
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=GEN_CASE["seed"], lm_head=True)
+    rng = np.random.Generator(np.random.PCG64(GEN_CASE["prompt_seed"]))
+    grids = GEN_CASE["grids"]
+    ids = torch.tensor([Q.make_prompt(rng, GEN_CASE["n_pre"], grids, GEN_CASE["n_post"])])
+    torch.manual_seed(GEN_CASE["pixel_seed"])
+    px = torch.randn(sum(t * h * w for t, h, w in grids), 1176)
+    return cfg, sd, ids, px, grids
+
+
+def test_greedy_generate_golden():
+    """The oracle's greedy decode reproduces the committed token ids (tests/golden/greedy_generate.json, written by
+    this file's __main__ after the transformers check below passed in the build container)."""
+    with open(os.path.join(GOLDEN, "greedy_generate.json")) as fh:
+        gold = json.load(fh)
+    cfg, sd, ids, px, grids = _gen_case()
+    with torch.no_grad():
+        assert Q.greedy_generate(sd, cfg, ids, px, grids, max_new_tokens=GEN_CASE["max_new"]) == gold["tokens"]
+        stop = gold["tokens"][3]
+        got = Q.greedy_generate(sd, cfg, ids, px, grids, max_new_tokens=GEN_CASE["max_new"], eos_token_ids=(stop,))
+        assert got == gold["tokens"][:4]
+
+
+def test_greedy_generate_vs_transformers():
+    """`model.generate(do_sample=False)` of the container's transformers (KV cache, GenerationMixin stop rules) against
+    the oracle's cache-free loop, token for token.  transformers 5.x computes a different temporal position for image
+    tokens than the reference's pin (4.51) and in-tree rope2d.get_rope_index_25; the reference-equal `rope_index`
+    (pinned bit-exactly above) is substituted so that the comparison is about the decode loop."""
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLForConditionalGeneration as M
+    cfg, sd, ids, px, grids = _gen_case()
+    vc, tc = _hf_cfgs(cfg)
+    c = Qwen2_5_VLConfig(text_config=tc.to_dict(), vision_config=vc.to_dict(), image_token_id=151655,
+                         video_token_id=151656, vision_start_token_id=151652, tie_word_embeddings=False)
+    m = M._from_config(c, attn_implementation="eager").float().eval()
+    msd = {}
+    for k, v in sd.items():
+        if k.startswith("visual."):
+            msd["model." + k] = v
+        elif k == "model.latent_queries":
+            continue
+        elif k.startswith("model."):
+            msd["model.language_model." + k[len("model."):]] = v
+        else:
+            msd[k] = v
+    m.load_state_dict(msd, strict=True)
+    m.model.get_rope_index = lambda input_ids, **kw: Q.rope_index(input_ids, kw["image_grid_thw"])
+    kw = dict(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=px, image_grid_thw=torch.tensor(grids),
+              do_sample=False, pad_token_id=151643, mm_token_type_ids=(ids == 151655).int())
+    with torch.no_grad():
+        ref = m.generate(max_new_tokens=GEN_CASE["max_new"], eos_token_id=[151645, 151643], **kw)[0, ids.shape[1]:].tolist()
+        mine = Q.greedy_generate(sd, cfg, ids, px, grids, max_new_tokens=GEN_CASE["max_new"])
+        assert ref == mine
+        stop = mine[3]  # stop rule: the eos id is emitted, then generation ends
+        ref2 = m.generate(max_new_tokens=GEN_CASE["max_new"], eos_token_id=[stop], **kw)[0, ids.shape[1]:].tolist()
+        assert ref2 == mine[:4] == Q.greedy_generate(sd, cfg, ids, px, grids, max_new_tokens=GEN_CASE["max_new"],
+                                                      eos_token_ids=(stop,))
+
+
+if __name__ == "__main__":
+    # refresh tests/golden/greedy_generate.json (build container; run the transformers check first)
+    test_greedy_generate_vs_transformers()
+    cfg, sd, ids, px, grids = _gen_case()
+    with torch.no_grad():
+        toks = Q.greedy_generate(sd, cfg, ids, px, grids, max_new_tokens=GEN_CASE["max_new"])
+    with open(os.path.join(GOLDEN, "greedy_generate.json"), "w") as fh:
+        json.dump({"case": GEN_CASE, "tokens": toks}, fh)
+    print("wrote greedy_generate.json", toks)

@@ -93,3 +93,99 @@ def test_real_width_shallow():
     gpp = [[(1, 28, 28)], [(1, 28, 28)]]
     prompts = [Q.make_prompt(rng, 24, gs, 80 - 10 * i) for i, gs in enumerate(gpp)]  # S = 304 / 294
     _check_latents(s2, sd, cfg, prompts, gpp, 4)
+
+
+# ------------------------------------------------------------------------------------------------ greedy decode
+MARGIN = 0.15  # logit units: bf16 logits (|x| ~ 4-5, ulp 2^-6) on a bf16 forward vs the fp32 oracle
+
+
+def _check_generate(s2, sd, cfg, prompts, gpp, seed, max_new, eos):
+    """Teacher-forced parity of the greedy decode: with OUR prefix, the token we picked must be the oracle's argmax or
+    within MARGIN of it (bf16 near-ties); the stop rule and the KV-reuse latents are checked exactly / to TOL."""
+    from oracle import qwen_oracle as Q
+    all_grids = [g for gs in gpp for g in gs]
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(sum(t * h * w for t, h, w in all_grids), 1176, generator=g).bfloat16().cuda()
+    out, lat, passes = s2.generate(prompts, px, all_grids, max_new_tokens=max_new, eos_token_ids=eos, with_latents=True)
+    assert passes == max(len(o) for o in out) - 1  # the pass after the last sampled token is never run
+    off_p, exact, total = 0, 0, 0
+    full_prompts = []
+    for b, (ids, gs) in enumerate(zip(prompts, gpp)):
+        npb = sum(t * h * w for t, h, w in gs)
+        pxb = px[off_p:off_p + npb]
+        off_p += npb
+        assert 1 <= len(out[b]) <= max_new
+        assert all(t not in eos for t in out[b][:-1]), "generation continued past an eos id"
+        assert out[b][-1] in eos or len(out[b]) == max_new, "generation stopped early"
+        cur = torch.tensor([ids])
+        with torch.no_grad():
+            feats = Q.vit_forward(sd, cfg, pxb.float(), gs)
+            for tok in out[b]:
+                lg = Q.next_token_logits(sd, cfg, cur, feats, gs)
+                gap = float(lg.max() - lg[tok])
+                assert gap <= MARGIN, ("env %d picked %d, oracle argmax %d, gap %.3f" % (b, tok, int(lg.argmax()), gap))
+                exact += int(int(lg.argmax()) == tok)
+                total += 1
+                cur = torch.cat([cur, torch.tensor([[tok]])], dim=1)
+            ref = Q.generate_latents(sd, cfg, cur, pxb.float(), gs)
+        e = _rel(lat[b], ref[0])
+        print("generate env", b, "tokens", out[b], "latent rel err (KV reuse)", e)
+        assert e < TOL, e
+        full_prompts.append(list(ids) + list(out[b]))
+    assert exact >= 0.6 * total, (exact, total)
+    # the cache-extension latents equal our own re-prefill of prompt + generated ids (the reference's route)
+    lat2 = s2.generate_latents(full_prompts, px, all_grids)
+    e2 = _rel(lat, lat2)
+    print("KV-reuse vs re-prefill latents rel", e2, "exact", exact, "/", total, "passes", passes)
+    assert e2 < 1e-2, e2
+    return out
+
+
+def _setup_gen(cfg, seed):
+    from internnav_b200.qwen import System2
+    from oracle import qwen_oracle as Q
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = Q.make_s2_state_dict(cfg, seed=seed, lm_head=True)
+    s2 = System2(cfg, device="cuda:0")
+    s2.load_state_dict(sd)
+    return s2, {k: v.cuda() for k, v in sd.items()}
+
+
+def test_generate_tiny():
+    from oracle import qwen_oracle as Q
+    cfg = Q.tiny_cfg()
+    s2, sd = _setup_gen(cfg, 5)
+    rng = np.random.Generator(np.random.PCG64(3))
+    gpp = [[(1, 8, 12)], [(1, 16, 16), (1, 4, 4)], [(1, 4, 8)]]
+    prompts = [Q.make_prompt(rng, 6 + 2 * i, gs, 10 + 3 * i) for i, gs in enumerate(gpp)]
+    out = _check_generate(s2, sd, cfg, prompts, gpp, 0, 8, ())          # budget-limited, ragged prompts
+    # golden: env 0 is the committed single-prompt case of tests/golden/greedy_generate.json (same seeds)
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "greedy_generate.json")) as fh:
+        gold = json.load(fh)["tokens"]
+    agree = sum(int(a == b) for a, b in zip(out[0], gold))
+    print("golden agreement", agree, "/", len(out[0]))
+    stop = out[0][2]
+    out2 = _check_generate(s2, sd, cfg, prompts, gpp, 0, 8, (stop,))     # env 0 stops after 3 tokens, the others go on
+    assert out2[0] == out[0][:3]
+    assert any(len(o) > 3 for o in out2[1:]) or all(stop in o for o in out2[1:])
+
+
+def test_generate_real_width_shallow():
+    from oracle import qwen_oracle as Q
+    cfg = dict(Q.QWEN25VL_7B)
+    cfg.update(v_depth=2, fullatt=[1], layers=2)
+    s2, sd = _setup_gen(cfg, 6)
+    rng = np.random.Generator(np.random.PCG64(11))
+    gpp = [[(1, 28, 28)], [(1, 28, 28)]]
+    prompts = [Q.make_prompt(rng, 24, gs, 80 - 10 * i) for i, gs in enumerate(gpp)]
+    _check_generate(s2, sd, cfg, prompts, gpp, 7, 5, (151645, 151643))
+
+
+def test_generate_requires_lm_head():
+    from oracle import qwen_oracle as Q
+    cfg = Q.tiny_cfg()
+    s2, _ = _setup(cfg, 1, vocab_rows=512)
+    with pytest.raises(RuntimeError):
+        s2.generate([[1, 2, 3]], torch.zeros(0, 1176), [], max_new_tokens=2)
