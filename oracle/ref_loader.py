@@ -107,3 +107,74 @@ def load_reference_rope2d():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
+
+
+def load_reference_agent(policy_factory, sleep_scale=0.01):
+    """Import the reference's own `internnav/agent/internvla_n1_agent.py` (class InternVLAN1Agent, untouched) with the
+    heavy / absent imports replaced by shims, so that its step()/reset()/S2-thread state machine can be driven by a
+    scripted policy (oracle/gen_golden_agent.py):
+
+      * gym.spaces.Box, imageio -- absent from the image, used only for a class attribute / debug videos;
+      * internnav.model.get_policy / get_config -- return `policy_factory` (the scripted stand-in for
+        InternVLAN1Net, whose real version needs a checkpoint) and a pass-through config;
+      * internnav.model.utils.misc.set_random_seed -- the real one pulls in the logging stack; restated (4 lines);
+      * the module's `time` is wrapped so that every sleep is `sleep_scale` times as long (the polling intervals
+        0.5 / 0.2 / 0.01 s of L143, L205, L271, L274 only pace the handshake with the S2 thread).
+    internnav.agent.base, internnav.configs.agent, internnav.configs.model.base_encoders and
+    internnav.model.utils.vln_utils are the reference's own files."""
+    import importlib.util
+    import time as _time
+
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "internnav" or k.startswith("internnav.")}
+    for k in saved:
+        del sys.modules[k]
+    had = {}
+    try:
+        for name, rel in [("internnav", ""), ("internnav.agent", "agent"), ("internnav.configs", "configs"),
+                          ("internnav.configs.model", "configs/model"), ("internnav.model", "model"),
+                          ("internnav.model.utils", "model/utils")]:
+            _bare_package(name, os.path.join(REF, "internnav", rel))
+        gym = types.ModuleType("gym")
+        gym.spaces = types.ModuleType("gym.spaces")
+        gym.spaces.Box = lambda **kw: ("Box", kw)
+        imageio = types.ModuleType("imageio")
+        imageio.get_writer = lambda *a, **k: None
+        had = {k: sys.modules.get(k) for k in ("gym", "gym.spaces", "imageio")}
+        sys.modules.update({"gym": gym, "gym.spaces": gym.spaces, "imageio": imageio})
+        misc = types.ModuleType("internnav.model.utils.misc")
+
+        def set_random_seed(seed):  # internnav/model/utils/misc.py L18-22
+            import random
+
+            import numpy as np
+            import torch
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+        misc.set_random_seed = set_random_seed
+        sys.modules["internnav.model.utils.misc"] = misc
+        model_pkg = sys.modules["internnav.model"]
+        model_pkg.get_policy = lambda name: policy_factory
+        model_pkg.get_config = lambda name: (lambda model_cfg=None: model_cfg)
+        mod = importlib.import_module("internnav.agent.internvla_n1_agent")
+
+        class _FastTime:
+            def __getattr__(self, k):
+                return getattr(_time, k)
+
+            @staticmethod
+            def sleep(s):
+                _time.sleep(s * sleep_scale)
+        mod.time = _FastTime()
+        return mod
+    finally:
+        for k in [k for k in sys.modules if k == "internnav" or k.startswith("internnav.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+        for k, v in had.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
