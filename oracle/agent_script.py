@@ -18,8 +18,9 @@ import numpy as np
 
 
 def make_obs(k, size=8):
-    rgb = np.full((size, size, 3), k % 256, dtype=np.uint8)
-    depth = np.full((size, size, 1), (k % 64) / 100.0, dtype=np.float32)
+    h, w = (size, size) if isinstance(size, int) else size
+    rgb = np.full((h, w, 3), k % 256, dtype=np.uint8)
+    depth = np.full((h, w, 1), (k % 64) / 100.0, dtype=np.float32)
     return {"rgb": rgb, "depth": depth, "instruction": "go to frame %d" % k}
 
 

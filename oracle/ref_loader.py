@@ -178,3 +178,58 @@ def load_reference_agent(policy_factory, sleep_scale=0.01):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def load_reference_policy():
+    """Import the reference's `internvla_n1_policy.py` (class InternVLAN1Net, untouched) for driving its HOST logic --
+    init_prompts / reset / parse_actions / step_no_infer / s2_step / s1_step_latent -- with scripted collaborators
+    (oracle/policy_script.py).  The model module it imports (internvla_n1.py -> diffusers, NextDiT) is replaced by a
+    stub holding the two names the policy file references at class-definition time; the returned subclass only adds
+    a constructor that skips from_pretrained and a fixed `device`."""
+    import importlib
+
+    import torch
+    from transformers import PretrainedConfig
+
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF)
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "internnav" or k.startswith("internnav.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        for name, rel in [("internnav", ""), ("internnav.model", "model"), ("internnav.model.basemodel", "model/basemodel"),
+                          ("internnav.model.basemodel.internvla_n1", "model/basemodel/internvla_n1"),
+                          ("internnav.configs", "configs"), ("internnav.configs.model", "configs/model"),
+                          ("internnav.model.utils", "model/utils")]:
+            _bare_package(name, os.path.join(REF, "internnav", rel))
+        stub = types.ModuleType("internnav.model.basemodel.internvla_n1.internvla_n1")
+
+        class InternVLAN1ModelConfig(PretrainedConfig):
+            model_type = "internvla_n1_stub"
+
+        stub.InternVLAN1ModelConfig = InternVLAN1ModelConfig
+        stub.InternVLAN1ForCausalLM = type("InternVLAN1ForCausalLM", (), {})
+        sys.modules[stub.__name__] = stub
+        mod = importlib.import_module("internnav.model.basemodel.internvla_n1.internvla_n1_policy")
+
+        class ScriptedNet(mod.InternVLAN1Net):
+            def __init__(self, model, processor, num_history=8, resize_w=384, resize_h=384, continuous_traj=True):
+                torch.nn.Module.__init__(self)
+                self.__dict__["model"] = model
+                self.processor = processor
+                self.tokenizer = processor.tokenizer
+                self.init_prompts()
+                self.num_history, self.resize_w, self.resize_h = num_history, resize_w, resize_h
+                self.continuous_traj = continuous_traj
+                self.rgb_list, self.depth_list, self.pose_list = [], [], []
+                self.episode_idx = 0
+                self.conversation_history = []
+                self.llm_output = ""
+
+            device = property(lambda self: torch.device("cpu"))
+
+        return mod, ScriptedNet
+    finally:
+        for k in [k for k in sys.modules if k == "internnav" or k.startswith("internnav.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
