@@ -146,13 +146,16 @@ class InternVLAN1Policy:
             ep = self.episodes[env_ids[j]]
             ep.llm_output = self.processor.tokenizer.decode(out.generated[n], skip_special_tokens=True)
             res = S2Output()
-            if re.search(r"\d", ep.llm_output):       # pixel goal "y x" -> [x, y] plus the latent plan (L179-190)
-                coord = [int(c) for c in re.findall(r"\d+", ep.llm_output)]
-                res.output_pixel = np.array([int(coord[1]), int(coord[0])])
-                res.output_latent = out.latents[n:n + 1]
-            else:
-                res.output_action = parse_actions(ep.llm_output)
-            results[j] = res
+            try:
+                if re.search(r"\d", ep.llm_output):   # pixel goal "y x" -> [x, y] plus the latent plan (L179-190)
+                    coord = [int(c) for c in re.findall(r"\d+", ep.llm_output)]
+                    res.output_pixel = np.array([int(coord[1]), int(coord[0])])
+                    res.output_latent = out.latents[n:n + 1]
+                else:
+                    res.output_action = parse_actions(ep.llm_output)
+                results[j] = res
+            except Exception as exc:  # noqa: BLE001 -- e.g. an answer with a single number (IndexError at L181 as well)
+                results[j] = exc
         return results
 
     # ------------------------------------------------------------------ System 1

@@ -24,7 +24,7 @@ def test_dual_system_step_matches_oracle_chain():
     model.load_parts(s2_sd, s1_sd)
     assert model.get_n_query() == 4 and model.get_system1_type() == "navdp_async"
     with pytest.raises(NotImplementedError):
-        model.generate()
+        model.forward()
 
     B = 2
     rng = np.random.Generator(np.random.PCG64(8))
@@ -34,6 +34,8 @@ def test_dual_system_step_matches_oracle_chain():
     n_p = sum(t * h * w for t, h, w in grids)
     g = torch.Generator().manual_seed(2)
     px = torch.randn(n_p, 1176, generator=g).bfloat16().cuda()
+    with pytest.raises(RuntimeError):   # this state_dict has no lm_head.weight: greedy decode must refuse, not improvise
+        model.generate(prompts, px, grids, max_new_tokens=4)
     inp = weights.make_inputs(9, B=B, K=20)
     rgb, dep = inp["rgb"].cuda(), inp["depth"].cuda()
     x0, nz = inp["x_init"].cuda(), inp["step_noise"].cuda()

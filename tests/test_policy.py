@@ -137,3 +137,35 @@ def test_look_down_needs_a_previous_answer():
     o = agent_script.make_obs(0, size=(24, 32))
     res = pol.s2_step([0], [o["rgb"]], [o["depth"]], [None], [o["instruction"]], None, [True])
     assert isinstance(res[0], AssertionError)
+
+
+def test_malformed_pixel_answer_is_reported_per_environment():
+    """An answer with digits but fewer than two numbers raises IndexError inside the reference's s2_step (L181); here
+    the environment that produced it gets the exception, its batch neighbours are unaffected, and the agent's retry
+    rule (reset, retry without look_down, then STOP) applies to it alone."""
+    from internnav_b200.agent import InternVLAN1Agent
+    from internnav_b200.policy import InternVLAN1Policy
+    traces = [dict(answers=["7"], trajs=TRACES[0]["trajs"]), dict(answers=["↑→"], trajs=TRACES[0]["trajs"])]
+    model = BatchedScriptedModel(traces)
+    pol = InternVLAN1Policy(model, policy_script.FakeProcessor(), num_envs=2)
+    obs = [agent_script.make_obs(0, size=(24, 32)) for _ in range(2)]
+    model.order = [0, 1]
+    res = pol.s2_step([0, 1], [o["rgb"] for o in obs], [o["depth"] for o in obs], [None, None],
+                      [o["instruction"] for o in obs], None, [False, False])
+    assert isinstance(res[0], IndexError) and res[1].output_action == [1, 3]
+
+    class Ordered:  # lets the scripted model know which environments a call serves
+        def __init__(self, pol):
+            self.pol = pol
+
+        def __getattr__(self, k):
+            return getattr(self.pol, k)
+
+        def s2_step(self, env_ids, *a):
+            model.order = list(env_ids)
+            return self.pol.s2_step(env_ids, *a)
+    pol2 = InternVLAN1Policy(model, policy_script.FakeProcessor(), num_envs=2)
+    ag = InternVLAN1Agent(Ordered(pol2), num_envs=2, infer_mode="sync")
+    ag.reset()
+    out = ag.step(obs)
+    assert [o["action"] for o in out] == [[0], [1]]      # env 0: two failures -> STOP; env 1: first arrow
