@@ -10,8 +10,9 @@ tensors.  Everything is batched over B independent environments, each treated ex
 KV cache; `generate_with_latents()` additionally extends that cache by the TRAJ tokens, which replaces the reference's
 second full prefill in `generate_latents(output_ids, ...)` (policy L187-190).
 
-Not built yet: the NextDiT System-1 branch and the training `forward` -- calling them raises
-NotImplementedError rather than falling back to anything slower.
+`forward()` is the training forward of the navdp_async branch on a collated batch, forward only (no backward kernels yet).
+
+Not built yet: the NextDiT System-1 branch and the backward pass -- there is no fallback for either.
 """
 from types import SimpleNamespace
 
@@ -167,9 +168,41 @@ class InternVLAN1ForCausalLM:
         return self.generate(input_ids, pixel_values, image_grid_thw, max_new_tokens=max_new_tokens, with_latents=True,
                              return_dict_in_generate=True, **kw)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("the full training forward/backward (SURVEY.md §8 row a13) is not built: the System-1 "
-                                  "loss is available forward-only as s1_training_loss(); no fallback")
+    def traj_hidden_states(self, input_ids, attention_mask, pixel_values, image_grid_thw, t_s_pos):
+        """System-2 half of the training forward (internvla_n1.py L128-235) for a collated batch
+        (internvla_n1_lerobot_dataset.py L1155-1277: every sample ends with n_query TRAJ tokens at t_s_pos[b], then
+        padding; attention_mask = input_ids != pad).  Causal attention makes the states at the TRAJ positions a function
+        of the unmasked tokens before them only, and masked tokens are invisible as keys and skipped by get_rope_index,
+        so this is the latent-plan prefill over the unmasked prefix of each sample.  -> [B, n_query, hidden]"""
+        rows = self._prompts(input_ids)
+        nq = self.config.n_query
+        mask = None if attention_mask is None else \
+            (attention_mask.tolist() if torch.is_tensor(attention_mask) else attention_mask)
+        prompts = []
+        for b, row in enumerate(rows):
+            t = int(t_s_pos[b])
+            if row[t:t + nq] != [TRAJ_TOKEN_INDEX] * nq:
+                raise ValueError("sample %d: input_ids[t_s_pos : t_s_pos + n_query] are not the TRAJ tokens" % b)
+            keep = [True] * len(row) if mask is None else [bool(v) for v in mask[b]]
+            if any(tok == IMAGE_TOKEN_INDEX and keep[i] for i, tok in enumerate(row) if i >= t + nq):
+                raise NotImplementedError("image tokens after the TRAJ tokens (not produced by the reference collator)")
+            prompts.append([tok for i, tok in enumerate(row[:t]) if keep[i]])
+        return self.generate_latents(prompts, pixel_values, image_grid_thw)
+
+    def forward(self, input_ids=None, attention_mask=None, labels=None, t_s_pos=None, pixel_values=None,
+                image_grid_thw=None, traj_images=None, traj_depths=None, video_frame_num=None, traj_poses=None,
+                noise=None, timesteps=None, **hf_kwargs):
+        """Training forward of the navdp_async branch (internvla_n1.py L58-318) on a collated batch -> namespace(loss,
+        logits=None, traj_hidden_states).  FORWARD ONLY: there are no backward kernels yet, so the
+        loss carries no graph; `logits` (computed but unused by this branch in the reference, L229) are not produced.
+        `noise` / `timesteps` inject the draws of `sample_noise` (navdp.py L165-175) for parity tests."""
+        if labels is None or t_s_pos is None or traj_images is None:
+            raise NotImplementedError("forward() implements the training branch (labels + t_s_pos + traj_* given); for "
+                                      "inference use generate() / generate_latents() / generate_traj()")
+        hs = self.traj_hidden_states(input_ids, attention_mask, pixel_values, image_grid_thw, t_s_pos)
+        loss = self.s1_training_loss(hs, traj_images, traj_depths, traj_poses, video_frame_num, noise=noise,
+                                     timesteps=timesteps)
+        return SimpleNamespace(loss=loss, logits=None, traj_hidden_states=hs)
 
     __call__ = forward
 

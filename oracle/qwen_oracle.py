@@ -155,8 +155,9 @@ def vit_forward(sd, cfg, pixel_values, grid_thw, p="visual."):
 
 
 # ------------------------------------------------------------------------------------------------ decoder
-def text_forward(sd, cfg, inputs_embeds, position_ids, p="model."):
-    """Qwen2_5_VLTextModel.forward, full causal attention, no cache; returns the final-norm hidden states [B,S,H]."""
+def text_forward(sd, cfg, inputs_embeds, position_ids, p="model.", key_mask=None):
+    """Qwen2_5_VLTextModel.forward, full causal attention, no cache; returns the final-norm hidden states [B,S,H].
+    `key_mask` [B,S] bool (the 2-D attention_mask of a padded batch): masked keys are invisible to every query."""
     x = inputs_embeds
     dt = x.dtype
     B, S, H = x.shape
@@ -184,6 +185,9 @@ def text_forward(sd, cfg, inputs_embeds, position_ids, p="model."):
         v = v.repeat_interleave(heads // kvh, dim=1)
         s = (q @ k.transpose(2, 3)) * hd ** -0.5
         s = s.masked_fill(mask, float("-inf"))
+        if key_mask is not None:
+            s = s.masked_fill(~key_mask.to(s.device)[:, None, None, :], float("-inf"))
+            s = s.masked_fill(~key_mask.to(s.device)[:, None, :, None], 0.0)  # padded queries: any finite row will do
         a = torch.softmax(s, dim=-1, dtype=torch.float32).to(dt) @ v
         a = a.transpose(1, 2).reshape(B, S, heads * hd)
         x = x + F.linear(a, sd[b + "self_attn.o_proj.weight"].to(dt))
@@ -242,6 +246,36 @@ def greedy_generate(sd, cfg, input_ids, pixel_values, image_grid_thw, max_new_to
         if tok in eos_token_ids:
             break
     return (out, logs) if return_logits else out
+
+
+def training_traj_states(sd, cfg, input_ids, attention_mask, pixel_values, image_grid_thw, t_s_pos):
+    """The System-2 half of the training forward (internvla_n1.py L128-235) on a collated batch
+    (internvla_n1_lerobot_dataset.py L1155-1277): input_ids [B,S] right-padded, each sample ending with n_query TRAJ
+    tokens at t_s_pos[b]; attention_mask = input_ids != pad.  Embeds, splices image features (masked_scatter order) and
+    `latent_queries` at the TRAJ positions (L166-172), get_rope_index with the mask (masked positions keep 1), runs the
+    decoder over the padded batch and gathers hidden[b, t_s_pos[b] : t_s_pos[b] + n_query].  -> [B, n_query, H]"""
+    dt = pixel_values.dtype
+    emb = sd["model.embed_tokens.weight"]
+    x = emb[input_ids.to(emb.device)].to(dt)
+    feats = vit_forward(sd, cfg, pixel_values, image_grid_thw)
+    x[(input_ids == IMAGE_TOKEN_INDEX).to(x.device)] = feats
+    nq = cfg["n_query"]
+    lat = sd["model.latent_queries"].to(dt).reshape(nq, -1)
+    traj_idx = input_ids == TRAJ_TOKEN_INDEX
+    x[traj_idx.to(x.device)] = lat.repeat(input_ids.shape[0], 1)
+    B, S = input_ids.shape
+    pos = torch.ones(3, B, S, dtype=torch.long)
+    img = 0
+    grids = torch.as_tensor(image_grid_thw).reshape(-1, 3)
+    for b in range(B):
+        keep = attention_mask[b].bool()
+        ids_b = input_ids[b][keep].unsqueeze(0)
+        n_img = int(((ids_b[0, :-1] == VISION_START) & (ids_b[0, 1:] == IMAGE_TOKEN_INDEX)).sum())
+        pb, _ = rope_index(ids_b, grids[img:img + n_img], cfg["v_merge"])
+        img += n_img
+        pos[:, b, keep] = pb[:, 0]
+    hs = text_forward(sd, cfg, x, pos.to(x.device), key_mask=attention_mask.bool())
+    return torch.stack([hs[b, t_s_pos[b]: t_s_pos[b] + nq] for b in range(B)])
 
 
 # ------------------------------------------------------------------------------------------------ synthetic weights

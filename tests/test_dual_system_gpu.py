@@ -63,3 +63,52 @@ def test_dual_system_step_matches_oracle_chain():
     pol = InternVLAN1Net(model)
     outs = pol.s1_step_latent(rgb, dep, mine_lat)
     assert len(outs) == B and all(isinstance(o.idx, list) for o in outs)
+
+
+def test_training_forward_from_collated_batch():
+    """SURVEY §8 row a13, forward: a collated dual-system batch (TRAJ tokens appended, right padding, ragged frame counts)
+    through InternVLAN1ForCausalLM.forward vs the oracle chain -- padded-batch decoder with latent_queries at the TRAJ
+    positions (qwen_oracle.training_traj_states) -> navdp_oracle.s1_training_loss -- with the noise draws injected."""
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from internnav_b200.manifest import random_navdp_state_dict
+    from internnav_b200.training import collate_traj_batch
+    from oracle import navdp_oracle as O, qwen_oracle as Q
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = Q.tiny_cfg()
+    s2_sd = Q.make_s2_state_dict(cfg, seed=13, vocab_rows=512)
+    s1_sd = random_navdp_state_dict(seed=14, vlm_token_dim=cfg["hidden"])
+    model = InternVLAN1ForCausalLM(cfg, device="cuda:0")
+    model.load_parts(s2_sd, s1_sd)
+    rng = np.random.Generator(np.random.PCG64(15))
+    g = torch.Generator().manual_seed(16)
+    gpp = [[(1, 8, 12)], [(1, 16, 16), (1, 4, 8)], [(1, 4, 4)]]
+    frames = [3, 2, 1]
+    inst = []
+    for gs, f in zip(gpp, frames):
+        ids = torch.tensor([Q.make_prompt(rng, 6, gs, 15)])
+        n_p = sum(t * h * w for t, h, w in gs)
+        inst.append(dict(input_ids=ids, labels=torch.full_like(ids, -100), pixel_values=torch.randn(n_p, 1176, generator=g),
+                         image_grid_thw=torch.tensor(gs), traj_images=torch.rand(f, 224, 224, 3, generator=g),
+                         traj_depths=torch.rand(f, 224, 224, generator=g) * 5, traj_poses=torch.randn(f, 32, 3, generator=g) * 0.5))
+    batch = collate_traj_batch(inst)
+    B, fmax = len(inst), max(frames)
+    assert batch["traj_images"].shape == (B, fmax, 224, 224, 3) and batch["video_frame_num"].tolist() == frames
+    assert torch.equal(batch["traj_images"][2, 1], batch["traj_images"][2, 0])          # last frame repeated
+    noise = torch.randn(B * fmax, 32, 3, generator=g).cuda()
+    ts = torch.randint(0, 20, (B * fmax,), generator=g)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    dev["pixel_values"] = dev["pixel_values"].bfloat16()
+    out = model.forward(noise=noise, timesteps=ts, **dev)
+    s2_gpu = {k: v.cuda() for k, v in s2_sd.items()}
+    s1_gpu = {k: v.cuda().float() for k, v in s1_sd.items()}
+    with torch.no_grad():
+        hs = Q.training_traj_states(s2_gpu, cfg, batch["input_ids"], batch["attention_mask"], dev["pixel_values"].float(),
+                                    batch["image_grid_thw"], batch["t_s_pos"])
+        ref = O.s1_training_loss(s1_gpu, hs, dev["traj_images"], dev["traj_depths"], dev["traj_poses"],
+                                 dev["video_frame_num"], noise, ts.cuda())
+    e_h = _rel(out.traj_hidden_states, hs)
+    print("training forward: traj states rel err", e_h, "loss", float(out.loss), "oracle", float(ref))
+    assert e_h < 2e-2
+    assert abs(float(out.loss) - float(ref)) / float(ref) < 3e-2
+    with pytest.raises(ValueError):   # t_s_pos must point at the TRAJ tokens
+        model.forward(noise=noise, timesteps=ts, **{**dev, "t_s_pos": [p - 1 for p in batch["t_s_pos"]]})

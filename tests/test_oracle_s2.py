@@ -218,3 +218,62 @@ if __name__ == "__main__":
     with open(os.path.join(GOLDEN, "greedy_generate.json"), "w") as fh:
         json.dump({"case": GEN_CASE, "tokens": toks}, fh)
     print("wrote greedy_generate.json", toks)
+
+
+# ------------------------------------------------------------------------------------------------ training forward
+def collate(prompts, pad=151643, nq=4):
+    """process_input_with_traj_tokens + pad_sequence of the reference collator (internvla_n1_lerobot_dataset.py
+    L1155-1215): TRAJ tokens appended, right padding, attention_mask = input_ids != pad."""
+    rows = [list(p) + [Q.TRAJ_TOKEN_INDEX] * nq for p in prompts]
+    S = max(len(r) for r in rows)
+    ids = torch.tensor([r + [pad] * (S - len(r)) for r in rows])
+    return ids, ids.ne(pad), [len(p) for p in prompts]
+
+
+def test_training_states_equal_latent_prefill():
+    """The padded-batch training forward (TRAJ tokens inside the sequence, key padding mask, masked get_rope_index)
+    yields, at the TRAJ positions, exactly what generate_latents yields for each unpadded prompt -- the identity the
+    CUDA path's forward() relies on.  One prompt also holds the pad id in its middle (masked there, as the collator's
+    `input_ids.ne(pad)` does)."""
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=7, vocab_rows=256)
+    rng = np.random.Generator(np.random.PCG64(21))
+    gpp = [[(1, 8, 12)], [(1, 4, 8), (1, 8, 8)], [(1, 4, 4)]]
+    prompts = [Q.make_prompt(rng, 5 + 4 * i, gs, 18 - 6 * i) for i, gs in enumerate(gpp)]
+    prompts[2][3] = 151643
+    grids = [g for gs in gpp for g in gs]
+    torch.manual_seed(3)
+    px = torch.randn(sum(t * h * w for t, h, w in grids), 1176)
+    ids, mask, t_s_pos = collate(prompts)
+    with torch.no_grad():
+        full = Q.training_traj_states(sd, cfg, ids, mask, px, grids, t_s_pos)
+        off = 0
+        for b, (p, gs) in enumerate(zip(prompts, gpp)):
+            n = sum(t * h * w for t, h, w in gs)
+            kept = [t for t in p if t != 151643]
+            ref = Q.generate_latents(sd, cfg, torch.tensor([kept]), px[off:off + n], gs)
+            off += n
+            assert torch.allclose(full[b], ref[0], atol=2e-5, rtol=1e-5), (b, (full[b] - ref[0]).abs().max())
+
+
+def test_decoder_padding_mask_vs_transformers():
+    """text_forward(key_mask=...) against the transformers text model driven with a 2-D attention_mask (right padding),
+    compared on the unpadded positions."""
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLTextModel as TM
+    cfg = Q.tiny_cfg(vocab=2048)
+    sd = Q.make_s2_state_dict(cfg, seed=2)
+    _, tc = _hf_cfgs(cfg)
+    m = TM._from_config(tc, attn_implementation="eager").float().eval()
+    m.load_state_dict({k[len("model."):]: v for k, v in sd.items() if k.startswith("model.") and "latent_queries" not in k},
+                      strict=True)
+    torch.manual_seed(4)
+    B, S = 2, 24
+    emb = torch.randn(B, S, cfg["hidden"])
+    mask = torch.ones(B, S, dtype=torch.bool)
+    mask[1, 17:] = False
+    pos = torch.arange(S).view(1, 1, S).expand(3, B, S).clone()
+    pos[:, 1, 17:] = 1
+    with torch.no_grad():
+        ref = m(inputs_embeds=emb, position_ids=pos, attention_mask=mask.long()).last_hidden_state
+        mine = Q.text_forward(sd, cfg, emb, pos, key_mask=mask)
+    assert torch.allclose(ref[mask], mine[mask], atol=3e-4, rtol=1e-4), (ref[mask] - mine[mask]).abs().max()
