@@ -178,6 +178,28 @@ int n1_rope_index(const int32_t* input_ids_host, int len, const int32_t* grid_th
 int n1_vit_window_index(const int32_t* grid_thw_host, int n_img, int merge, int window, int32_t* window_index_host,
                         int32_t* cu_window_host, int32_t* n_cu, int32_t* pos_hw_host /* [n_patches, 2] or NULL */);
 
+/* ------------------------------------------------------------------------------------------------ frame preprocessing
+ * replaces: the Pillow resizes of the System-1 input preprocessing, per frame on the host in the reference:
+ *   np.array(Image.fromarray(rgb).resize((224, 224))) / 255.0
+ *   np.array(Image.fromarray(depth[:, :, 0]).resize((224, 224))) * 10.0, clipped at 5.0
+ *                                                         (internnav/agent/internvla_n1_agent.py L308-334)
+ * Pillow's default resampler (two-pass antialiased bicubic, 22-bit fixed point for 8-bit images, double accumulation
+ * for float images) is reproduced BIT-EXACTLY for a batch of frames already in HBM. */
+typedef struct n1_resize_plan_s* n1_resize_plan;
+int n1_resize_plan_create(int in_h, int in_w, int out_h, int out_w, n1_resize_plan* out, void* stream);
+void n1_resize_plan_destroy(n1_resize_plan p);
+size_t n1_resize_workspace_bytes(n1_resize_plan p, int n_frames, int is_float);
+/* src uint8 [n, in_h, in_w, 3] -> dst_f32 [n, out_h, out_w, 3] = resized / 255 and/or dst_u8 (either may be NULL) */
+int n1_resize_rgb_u8(n1_resize_plan p, const void* src_u8, int n_frames, void* dst_f32, void* dst_u8, void* ws,
+                     size_t ws_bytes, void* stream);
+/* src float [n, in_h, in_w] -> dst float [n, out_h, out_w] = resized * mul, values above clip_max set to clip_max */
+int n1_resize_f32(n1_resize_plan p, const void* src_f32, int n_frames, float mul, float clip_max, void* dst_f32,
+                  void* ws, size_t ws_bytes, void* stream);
+/* HOST-only: Pillow's precompute_coeffs + normalize_coeffs_8bpc for one axis.  bounds_host [out, 2] (first index,
+ * count); weights_host / fixed_host [out, ksize] with ksize returned in *ksize (capacity of both: out * capacity_k). */
+int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds_host, double* weights_host,
+                     int32_t* fixed_host, int32_t* ksize);
+
 /* ------------------------------------------------------------------------------------------------ accounting
  * Kernel-launch counters are always on; with n1_prof_enable(1) every GEMM launch is additionally bracketed by CUDA
  * events on its stream (bench.py's roofline pass -- not for timed runs).  n1_prof_read synchronises, returns the sums

@@ -86,10 +86,15 @@ class _Plan:
 
 
 class InternVLAN1Agent:
-    def __init__(self, policy, num_envs=1, infer_mode="sync", sys2_max_forward_step=8, width=640, height=480, hfov=79):
+    def __init__(self, policy, num_envs=1, infer_mode="sync", sys2_max_forward_step=8, width=640, height=480, hfov=79,
+                 preprocessor=None):
+        """`preprocessor`: an internnav_b200.preprocess.FramePreprocessor -- the goal / current frames of all
+        environments are then resized on the GPU in one batch (bit-identical to the per-frame Pillow calls of
+        `s1_frames`, which stay the default because they need no device)."""
         if infer_mode not in ("sync", "partial_async"):
             raise ValueError("Invalid mode: {}".format(infer_mode))
         self.policy = policy
+        self.preprocessor = preprocessor
         self.num_envs = num_envs
         self.mode = infer_mode
         self.sys2_max_forward_step = sys2_max_forward_step
@@ -191,6 +196,10 @@ class InternVLAN1Agent:
             if self.mode == "sync":                        # L335
                 rgbs = [obs[e]["rgb"] for e in to_s1]
                 depths = [obs[e]["depth"] * 10000.0 for e in to_s1]
+            elif self.preprocessor is not None:
+                r, d = self.preprocessor.s1_frames([self.plans[e].rgb for e in to_s1], [self.plans[e].depth for e in to_s1],
+                                                   [obs[e]["rgb"] for e in to_s1], [obs[e]["depth"] for e in to_s1])
+                rgbs, depths = [r[j:j + 1] for j in range(len(to_s1))], [d[j:j + 1] for j in range(len(to_s1))]
             else:
                 pairs = [s1_frames(self.plans[e].rgb, self.plans[e].depth, obs[e]["rgb"], obs[e]["depth"]) for e in to_s1]
                 rgbs, depths = [a for a, _ in pairs], [b for _, b in pairs]

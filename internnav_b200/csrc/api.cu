@@ -5,6 +5,7 @@
 
 #include "../../include/n1b200.h"
 #include "n1_ops.h"
+#include "resize.h"
 #include "s1_model.h"
 #include "s2_model.h"
 #include "weights.h"
@@ -21,6 +22,9 @@ struct n1_vit_plan_s {
 };
 struct n1_llm_plan_s {
   LlmPlan* p;
+};
+struct n1_resize_plan_s {
+  ResizePlan* p;
 };
 
 namespace {
@@ -316,6 +320,61 @@ int n1_llm_generate(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const
     r.tokens = tokens, r.lens = lens;
     h->s2.llm_generate(*p->p, ws, ws_bytes, B16(image_feats), eos, n_eos, pad_id, r, B16(latents), S(stream));
     if (passes) *passes = r.steps;
+  });
+}
+
+int n1_resize_plan_create(int in_h, int in_w, int out_h, int out_w, n1_resize_plan* out, void* stream) {
+  return guard([&] {
+    if (!out || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0) throw Error(N1_ERR_ARG, "n1_resize_plan_create: bad sizes");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) throw Error(N1_ERR_NO_DEVICE, "no CUDA device visible; n1b200 has no CPU fallback");
+    require_device(dev);
+    n1_resize_plan_s* w = new n1_resize_plan_s();
+    try {
+      w->p = new ResizePlan(in_h, in_w, out_h, out_w, S(stream));
+    } catch (...) {
+      delete w;
+      throw;
+    }
+    *out = w;
+  });
+}
+void n1_resize_plan_destroy(n1_resize_plan p) {
+  if (!p) return;
+  delete p->p;
+  delete p;
+}
+size_t n1_resize_workspace_bytes(n1_resize_plan p, int n, int is_float) {
+  return p && n > 0 ? p->p->workspace_bytes(n, is_float ? 1 : 3, is_float != 0) : 0;
+}
+int n1_resize_rgb_u8(n1_resize_plan p, const void* src, int n, void* dst_f32, void* dst_u8, void* ws, size_t ws_bytes,
+                     void* stream) {
+  return guard([&] {
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    if (ws_bytes < p->p->workspace_bytes(n, 3, false)) throw Error(N1_ERR_WORKSPACE, "n1_resize_rgb_u8: workspace too small");
+    resize_rgb_u8(*p->p, static_cast<const uint8_t*>(src), n, static_cast<float*>(dst_f32), static_cast<uint8_t*>(dst_u8),
+                  ws, S(stream));
+  });
+}
+int n1_resize_f32(n1_resize_plan p, const void* src, int n, float mul, float clip_max, void* dst, void* ws,
+                  size_t ws_bytes, void* stream) {
+  return guard([&] {
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    if (ws_bytes < p->p->workspace_bytes(n, 1, true)) throw Error(N1_ERR_WORKSPACE, "n1_resize_f32: workspace too small");
+    resize_f32(*p->p, static_cast<const float*>(src), n, mul, clip_max, static_cast<float*>(dst), ws, S(stream));
+  });
+}
+int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds, double* weights, int32_t* fixed,
+                     int32_t* ksize) {
+  return guard([&] {
+    if (!bounds || !weights || !fixed || !ksize) throw Error(N1_ERR_ARG, "n1_resize_coeffs: null outputs");
+    ResizeCoeffs c;
+    resize_coeffs(in_size, out_size, c);
+    if (c.ksize > capacity_k) throw Error(N1_ERR_ARG, "n1_resize_coeffs: capacity_k < " + std::to_string(c.ksize));
+    *ksize = c.ksize;
+    memcpy(bounds, c.bounds.data(), c.bounds.size() * sizeof(int32_t));
+    memcpy(weights, c.weights.data(), c.weights.size() * sizeof(double));
+    memcpy(fixed, c.fixed.data(), c.fixed.size() * sizeof(int32_t));
   });
 }
 

@@ -129,6 +129,10 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
     def rgbd_encoder(self, images, depths):
         """DAT_RGBD_Patch_Backbone.forward (navdp_backbone.py L151-202): [B,F,224,224,3], [B,F,224,224,1] -> [B,16F,384]."""
         B = images.shape[0]
+        want = (self.memory_size, self.image_size, self.image_size)
+        if tuple(images.shape[1:]) != want + (3,) or tuple(depths.shape[1:]) != want + (1,) or depths.shape[0] != B:
+            raise ValueError("rgbd_encoder takes images [B, %d, %d, %d, 3] and depths [B, %d, %d, %d, 1]; got %s and %s"
+                             % (want + want + (tuple(images.shape), tuple(depths.shape))))
         rgb = images.to(self._device, torch.float32).contiguous()
         dep = depths.to(self._device, torch.float32).contiguous()
         out = torch.empty(B, 16 * self.memory_size, self.token_dim, device=self._device, dtype=torch.bfloat16)
