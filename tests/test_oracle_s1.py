@@ -131,3 +131,31 @@ def test_oracle_vs_reference_modules(sd):
         assert torch.allclose(m.goal_compressor(m.vlm_embed_mlp(inp["latents"]), None), g, **TOL)
         k = torch.tensor([3])
         assert torch.allclose(m.predict_noise(inp["x_init"], k, g, r), O.predict_noise(sd, inp["x_init"], k, g, o), **TOL)
+
+
+def test_training_branch_forward_and_gradients_vs_reference(sd):
+    """Row a13, System-1 half: the oracle's forward_vlm_traj + masked MSE and ONE autograd backward through it against
+    tests/golden/s1_training_reference.npz -- prediction, loss, per-parameter gradient norms and seeded projections,
+    and the gradient w.r.t. the latent tokens, all produced by the reference's own module (oracle/gen_golden_training.py).
+    Also pins which parameters train at all: the RGB ViT is detached in the reference (navdp_backbone.py L170-171)."""
+    from oracle import gen_golden_training as G
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "s1_training_reference.npz"))
+    b = G.make_batch()
+    with torch.no_grad():
+        imgs, deps = G.dp_inputs(b)
+        f = b["traj_images"].shape[1]
+        hs_rep = b["hs"].unsqueeze(1).repeat(1, f, 1, 1).flatten(0, 1)
+        pred, _ = O.forward_vlm_traj(sd, hs_rep, imgs, deps, b["traj_poses"].flatten(0, 1), b["noise"], b["timesteps"])
+    assert np.allclose(pred.numpy(), gold["pred"], **TOL), np.abs(pred.numpy() - gold["pred"]).max()
+    loss, grads, g_hs = O.s1_training_grads(sd, b["hs"], b["traj_images"], b["traj_depths"], b["traj_poses"],
+                                            b["video_frame_num"], b["noise"], b["timesteps"])
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * max(1.0, float(gold["loss"]))
+    names = [str(n) for n in gold["grad_names"]]
+    assert sorted(grads) == sorted(names), set(grads) ^ set(names)
+    assert not any(k.startswith("rgbd_encoder.rgb_model.") for k in grads)
+    for n, norm, dot in zip(names, gold["grad_norms"], gold["grad_dots"]):
+        g = grads[n]
+        assert abs(float(g.norm()) - norm) <= 2e-4 * norm + 1e-9, (n, float(g.norm()), norm)
+        mine = float((g * G.probe(n, tuple(g.shape))).sum())
+        assert abs(mine - dot) <= 1e-3 * norm + 2e-4 * abs(dot) + 1e-7, (n, mine, dot)   # |g . probe| ~ |g|
+    assert np.allclose(g_hs.numpy(), gold["grad_hs"], atol=1e-7, rtol=2e-3), np.abs(g_hs.numpy() - gold["grad_hs"]).max()
