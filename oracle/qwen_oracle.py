@@ -278,6 +278,19 @@ def training_traj_states(sd, cfg, input_ids, attention_mask, pixel_values, image
     return torch.stack([hs[b, t_s_pos[b]: t_s_pos[b] + nq] for b in range(B)])
 
 
+def latent_query_grads(sd, cfg, input_ids, attention_mask, pixel_values, image_grid_thw, t_s_pos, grad_states):
+    """Backward of the System-2 half of the training step (row a13): the LLM is frozen, the only trainable tensor on
+    this side is `model.latent_queries` (internvla_n1_arch.py L123; written into the TRAJ positions at internvla_n1.py
+    L166-172).  Given d loss / d traj_hidden_states [B, n_query, H] (from navdp_oracle.s1_training_grads) returns
+    d loss / d latent_queries [1, n_query, H] by autograd through `training_traj_states`."""
+    leaf = sd["model.latent_queries"].detach().clone().requires_grad_(True)
+    full = dict(sd)
+    full["model.latent_queries"] = leaf
+    hs = training_traj_states(full, cfg, input_ids, attention_mask, pixel_values, image_grid_thw, t_s_pos)
+    (hs * grad_states.to(hs.dtype)).sum().backward()
+    return leaf.grad
+
+
 # ------------------------------------------------------------------------------------------------ synthetic weights
 def s2_shapes(cfg, lm_head=False):
     Hv, H = cfg["v_hidden"], cfg["hidden"]

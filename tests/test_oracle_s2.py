@@ -277,3 +277,43 @@ def test_decoder_padding_mask_vs_transformers():
         ref = m(inputs_embeds=emb, position_ids=pos, attention_mask=mask.long()).last_hidden_state
         mine = Q.text_forward(sd, cfg, emb, pos, key_mask=mask)
     assert torch.allclose(ref[mask], mine[mask], atol=3e-4, rtol=1e-4), (ref[mask] - mine[mask]).abs().max()
+
+
+def test_latent_query_gradient_vs_transformers():
+    """Backward oracle of the System-2 half (row a13): d loss / d latent_queries through the frozen decoder, against
+    autograd through the transformers text model fed the same embeddings / positions / padding mask (the gradient of
+    the embedding rows at the TRAJ positions, summed over the batch, is the gradient of the shared latent_queries)."""
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLTextModel as TM
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=9, vocab_rows=256)
+    _, tc = _hf_cfgs(cfg)
+    m = TM._from_config(tc, attn_implementation="eager").float().eval()
+    m.load_state_dict({k[len("model."):]: v for k, v in sd.items() if k.startswith("model.") and "latent_queries" not in k},
+                      strict=True)
+    rng = np.random.Generator(np.random.PCG64(31))
+    gpp = [[(1, 8, 12)], [(1, 4, 8)]]
+    prompts = [Q.make_prompt(rng, 5 + 6 * i, gs, 14 - 5 * i) for i, gs in enumerate(gpp)]
+    grids = [g for gs in gpp for g in gs]
+    torch.manual_seed(5)
+    px = torch.randn(sum(t * h * w for t, h, w in grids), 1176)
+    ids, mask, t_s_pos = collate(prompts)
+    G = torch.randn(len(prompts), cfg["n_query"], cfg["hidden"])
+    mine = Q.latent_query_grads(sd, cfg, ids, mask, px, grids, t_s_pos, G)
+    # transformers side: same embeddings and positions, autograd w.r.t. the embedding rows
+    with torch.no_grad():
+        emb = sd["model.embed_tokens.weight"][ids].clone()
+        emb[ids == Q.IMAGE_TOKEN_INDEX] = Q.vit_forward(sd, cfg, px, grids)
+        emb[ids == Q.TRAJ_TOKEN_INDEX] = sd["model.latent_queries"].reshape(cfg["n_query"], -1).repeat(len(prompts), 1)
+        pos = torch.ones(3, *ids.shape, dtype=torch.long)
+        img = 0
+        for b, gs in enumerate(gpp):
+            keep = mask[b]
+            pb, _ = Q.rope_index(ids[b][keep].unsqueeze(0), torch.tensor(gs))
+            pos[:, b, keep] = pb[:, 0]
+    emb.requires_grad_(True)
+    hs = m(inputs_embeds=emb, position_ids=pos, attention_mask=mask.long()).last_hidden_state
+    sel = torch.stack([hs[b, t:t + cfg["n_query"]] for b, t in enumerate(t_s_pos)])
+    (sel * G).sum().backward()
+    ref = torch.stack([emb.grad[b, t:t + cfg["n_query"]] for b, t in enumerate(t_s_pos)]).sum(0, keepdim=True)
+    assert mine.shape == ref.shape == (1, cfg["n_query"], cfg["hidden"])
+    assert torch.allclose(mine, ref, atol=2e-5, rtol=2e-3), (mine - ref).abs().max()
