@@ -226,6 +226,12 @@ int n1_op_gemm_row384(const void* A_bf16, int lda, const void* W_bf16, int ldw, 
 int n1_op_fused_mlp(const void* x_bf16, int ldx, const void* w1_bf16, const float* b1, const void* w2_bf16,
                     const float* b2, const void* residual_bf16, int ldr, void* out_bf16, int ldo, int M, int cluster,
                     void* stream);
+/* weight-streaming GEMM for M <= 64 rows (decode passes): out bf16 [M, N or N/2 for SwiGLU]; bias fp32 [N] / residual
+ * bf16 [M, ldr] may be NULL; act: 0 none, 1 GELU, 2 ReLU, 3 SwiGLU; ws: n1_op_gemm_skinny_workspace_bytes() of scratch */
+size_t n1_op_gemm_skinny_workspace_bytes(void);
+int n1_op_gemm_skinny(const void* a_bf16, int lda, const void* w_bf16, int ldw, void* out_bf16, int ldo, int M, int N,
+                      int K, const void* bias_f32, const void* residual_bf16, int ldr, int act, void* ws, size_t ws_bytes,
+                      void* stream);
 int n1_op_layernorm(const void* x_bf16, int ldx, void* y_bf16, int ldy, const float* w, const float* b, int rows, int D,
                     float eps, int rms, void* stream);
 /* q/k/v/o bf16 with row strides ld*; sequences fixed-length (cu_* NULL) or varlen (int32 prefix sums on device) */

@@ -62,6 +62,9 @@ SYMBOLS = {
                                   c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     "n1_op_fused_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                 c_int, c_int, c_void_p]),
+    "n1_op_gemm_skinny_workspace_bytes": (c_size_t, []),
+    "n1_op_gemm_skinny": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
                                 c_void_p]),
     "n1_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -140,6 +143,23 @@ def gemm(a, w, bias=None, gamma=None, residual=None, act=ACT_NONE, out_fp32=Fals
                            c_void_p(out.data_ptr()), out.stride(0), M, N, K, ptr(bias), ptr(gamma),
                            c_void_p(residual.data_ptr()) if residual is not None else None,
                            residual.stride(0) if residual is not None else 0, act, 1 if out_fp32 else 0, stream_ptr()))
+    return out
+
+
+def gemm_skinny(a, w, bias=None, residual=None, act=ACT_NONE, ws=None):
+    """Weight-streaming product for M <= 64 rows (decode passes): same result contract as gemm()."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N // 2 if act == ACT_SWIGLU else N, device=a.device, dtype=torch.bfloat16)
+    nb = lib().n1_op_gemm_skinny_workspace_bytes()
+    if ws is None:
+        ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    check(lib().n1_op_gemm_skinny(c_void_p(a.data_ptr()), a.stride(0), c_void_p(w.data_ptr()), w.stride(0), ptr(out),
+                                  out.stride(0), M, N, K, ptr(bias),
+                                  c_void_p(residual.data_ptr()) if residual is not None else None,
+                                  residual.stride(0) if residual is not None else 0, act, ptr(ws), nb, stream_ptr()))
     return out
 
 

@@ -446,6 +446,18 @@ int n1_op_fused_mlp(const void* x, int ldx, const void* w1, const float* b1, con
   });
 }
 
+size_t n1_op_gemm_skinny_workspace_bytes(void) { return gemm_skinny_workspace_bytes(); }
+int n1_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
+                      const void* bias, const void* residual, int ldr, int act, void* ws, size_t ws_bytes, void* stream) {
+  return guard([&] {
+    if (!a || !w || !out || !ws) throw Error(N1_ERR_ARG, "n1_op_gemm_skinny: null pointer");
+    if (ws_bytes < gemm_skinny_workspace_bytes()) throw Error(N1_ERR_WORKSPACE, "n1_op_gemm_skinny: workspace too small");
+    GemmEpilogue e;
+    e.bias = static_cast<const float*>(bias), e.residual = B16(residual), e.ldr = ldr, e.act = act;
+    if (!gemm_skinny_supported(M, N, K, e)) throw Error(N1_ERR_ARG, "n1_op_gemm_skinny: unsupported shape (M <= 64, N % 8, K % 8)");
+    gemm_skinny(B16(a), lda, B16(w), ldw, B16(out), ldo, M, N, K, e, static_cast<float*>(ws), S(stream));
+  });
+}
 int n1_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* w, const float* b, int rows, int D, float eps,
                     int rms, void* stream) {
   return guard([&] { layernorm(B16(x), ldx, B16(y), ldy, w, b, rows, D, eps, rms, S(stream)); });

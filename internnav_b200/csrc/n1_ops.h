@@ -69,6 +69,13 @@ void gemm_row384(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, c
 void fused_mlp_384(const bf16* x, int ldx, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
                    const bf16* residual, int ldr, bf16* out, int ldo, int M, int cluster, cudaStream_t stream);
 
+// Weight-streaming GEMM for M <= 64 rows (gemm_skinny.cu): same contract as gemm_bf16 for the epilogues the decode
+// passes use (bias, GELU / ReLU / SwiGLU, residual; bf16 out).  `ws`: gemm_skinny_workspace_bytes() of fp32 scratch.
+bool gemm_skinny_supported(int M, int N, int K, const GemmEpilogue& epi);
+size_t gemm_skinny_workspace_bytes();
+void gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, bf16* out, int ldo, int M, int N, int K,
+                 const GemmEpilogue& epi, float* ws, cudaStream_t stream);
+
 // Launch accounting (always on) and optional per-GEMM event timing (bench.py's roofline pass).
 struct ProfStats {
   double gemm_ms = 0, gemm_flops = 0;

@@ -240,3 +240,45 @@ def test_gemm_row384(L, M, K, use_ln, use_gamma):
     else:
         out = L.gemm_row384(a, w, bias, gamma=gamma, residual=res)
         assert _rel(out, y) < 6e-3
+
+
+SKINNY_VALIDATED = os.environ.get("N1_TEST_EXPERIMENTAL") == "1" or os.path.exists(
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_gemm_skinny_parity.log"))
+
+
+@pytest.mark.skipif(not SKINNY_VALIDATED, reason="gemm_skinny.cu has no GPU parity run on record yet (off by default: "
+                                                 "N1_SKINNY_GEMM=1 enables it in the decode passes)")
+@pytest.mark.parametrize("M,N,K,act,bias,res", [
+    (64, 3584, 3584, 0, False, True),      # o_proj
+    (64, 4608, 3584, 0, True, False),      # stacked qkv
+    (64, 37888, 3584, 3, False, False),    # gate/up interleaved, SwiGLU
+    (64, 3584, 18944, 0, False, True),     # down_proj
+    (3, 512, 256, 0, True, True),          # tiny config, ragged M, K not a multiple of the stage
+    (17, 1000, 328, 2, True, False),       # N % 32 != 0, K % 64 != 0, ReLU
+    (64, 152064, 3584, 0, False, False),   # lm_head
+    (1, 40, 72, 1, True, True),            # one row, GELU
+])
+def test_gemm_skinny(L, M, N, K, act, bias, res):
+    torch.manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda") * 0.1 if bias else None
+    n_out = N // 2 if act == 3 else N
+    r = torch.randn(M, n_out, device="cuda").bfloat16() if res else None
+    out = L.gemm_skinny(a, w, bias=b, residual=r, act=act)
+    ref = a.float() @ w.float().T
+    if b is not None:
+        ref = ref + b
+    if act == 3:
+        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+    elif act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    if r is not None:
+        ref = ref + r.float()
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    # and against the tcgen05 GEMM on the same operands: same epilogue order, so agreement to bf16 rounding
+    main = L.gemm(a, w, bias=b, residual=r, act=act)
+    assert _rel(out, main) < 4e-3, _rel(out, main)
