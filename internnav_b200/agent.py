@@ -32,6 +32,9 @@ class PerEnvPolicies:
     def __init__(self, policies):
         self.policies = list(policies)
 
+    def eval(self):
+        return self
+
     def reset(self, env_ids):
         for e in env_ids:
             self.policies[e].reset()

@@ -56,6 +56,22 @@ class InternVLAN1ForCausalLM:
                                                n_query=self.cfg["n_query"])
         self.model = _Model(navdp, self._s2, self.config)
 
+    @classmethod
+    def from_pretrained(cls, model_path, torch_dtype=None, attn_implementation=None, device_map=None, device=None, **kw):
+        """`InternVLAN1ForCausalLM.from_pretrained(model_path, torch_dtype=torch.bfloat16, attn_implementation=
+        "flash_attention_2", device_map={"": device})` (internvla_n1_policy.py L33-38): reads config.json and the weight
+        shards of a checkpoint directory and packs them into the library.  `torch_dtype` / `attn_implementation` are
+        accepted for signature compatibility (the kernels are bf16 with fp32 accumulation; attention is the library's)."""
+        from .checkpoint import read_checkpoint
+        if device is None:
+            device = (device_map or {}).get("", "cuda:0") if isinstance(device_map, dict) else (device_map or "cuda:0")
+        cfg, conf, sd = read_checkpoint(model_path)
+        model = cls(cfg, device=str(device), system1=conf.get("system1", "navdp_async"),
+                    predict_size=int(conf.get("predict_step_nums", 32)))
+        model.load_state_dict(sd)
+        model.name_or_path = model_path
+        return model
+
     # ------------------------------------------------------------------ reference-shaped accessors
     def get_model(self):
         return self.model

@@ -189,3 +189,51 @@ def test_generate_requires_lm_head():
     s2, _ = _setup(cfg, 1, vocab_rows=512)
     with pytest.raises(RuntimeError):
         s2.generate([[1, 2, 3]], torch.zeros(0, 1176), [], max_new_tokens=2)
+
+
+def test_from_pretrained_checkpoint_directory(tmp_path):
+    """`InternVLAN1ForCausalLM.from_pretrained(dir, torch_dtype=bf16, attn_implementation=..., device_map={"": dev})`
+    (internvla_n1_policy.py L33-38) on a checkpoint directory in the released layout (flat 4.51 config.json, sharded
+    safetensors, `model.navdp.*` keys): same latents and trajectories as the model loaded from the in-memory parts."""
+    import json
+    from safetensors.torch import save_file
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from internnav_b200.manifest import random_navdp_state_dict
+    from oracle import qwen_oracle as Q, weights
+    cfg = Q.tiny_cfg()
+    s2_sd = Q.make_s2_state_dict(cfg, seed=21, vocab_rows=512)
+    s1_sd = random_navdp_state_dict(seed=22, vlm_token_dim=cfg["hidden"])
+    full = {k: v.contiguous() for k, v in s2_sd.items()}
+    full.update({"model.navdp." + k: v.detach().cpu().contiguous() for k, v in s1_sd.items()})
+    names = sorted(full)
+    shard_a = {k: full[k] for k in names[::2]}
+    shard_b = {k: full[k] for k in names[1::2]}
+    save_file(shard_a, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file(shard_b, str(tmp_path / "model-00002-of-00002.safetensors"))
+    wm = {k: "model-00001-of-00002.safetensors" for k in shard_a}
+    wm.update({k: "model-00002-of-00002.safetensors" for k in shard_b})
+    (tmp_path / "model.safetensors.index.json").write_text(json.dumps({"weight_map": wm}))
+    conf = dict(model_type="internvla_n1", hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+                num_attention_heads=cfg["heads"], num_key_value_heads=cfg["kv_heads"], intermediate_size=cfg["inter"],
+                vocab_size=cfg["vocab"], rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"],
+                rope_scaling={"type": "mrope", "mrope_section": cfg["mrope"]}, n_query=4, system1="navdp_async",
+                vision_config=dict(depth=cfg["v_depth"], hidden_size=cfg["v_hidden"], num_heads=cfg["v_heads"],
+                                   intermediate_size=cfg["v_inter"], out_hidden_size=cfg["v_out"], patch_size=14,
+                                   temporal_patch_size=2, spatial_merge_size=2, window_size=112,
+                                   fullatt_block_indexes=cfg["fullatt"]))
+    (tmp_path / "config.json").write_text(json.dumps(conf))
+    a = InternVLAN1ForCausalLM.from_pretrained(str(tmp_path), torch_dtype=torch.bfloat16,
+                                               attn_implementation="flash_attention_2", device_map={"": "cuda:0"})
+    b = InternVLAN1ForCausalLM(cfg, device="cuda:0")
+    b.load_parts(s2_sd, s1_sd)
+    assert a.cfg == b.cfg and a.name_or_path == str(tmp_path)
+    rng = np.random.Generator(np.random.PCG64(23))
+    gs = [(1, 8, 12)]
+    prompts = [Q.make_prompt(rng, 7, gs, 12)]
+    px = torch.randn(96, 1176, generator=torch.Generator().manual_seed(1)).bfloat16().cuda()
+    la, lb = a.generate_latents(prompts, px, gs), b.generate_latents(prompts, px, gs)
+    assert torch.equal(la, lb)
+    inp = weights.make_inputs(24, B=1, K=20)
+    ta = a.generate_traj(la, inp["rgb"].cuda(), inp["depth"].cuda(), x_init=inp["x_init"].cuda(), step_noise=inp["step_noise"].cuda())
+    tb = b.generate_traj(lb, inp["rgb"].cuda(), inp["depth"].cuda(), x_init=inp["x_init"].cuda(), step_noise=inp["step_noise"].cuda())
+    assert torch.equal(ta, tb)
