@@ -159,3 +159,26 @@ def test_training_branch_forward_and_gradients_vs_reference(sd):
         mine = float((g * G.probe(n, tuple(g.shape))).sum())
         assert abs(mine - dot) <= 1e-3 * norm + 2e-4 * abs(dot) + 1e-7, (n, mine, dot)   # |g . probe| ~ |g|
     assert np.allclose(g_hs.numpy(), gold["grad_hs"], atol=1e-7, rtol=2e-3), np.abs(g_hs.numpy() - gold["grad_hs"]).max()
+
+
+def test_handwritten_backward_matches_autograd(sd):
+    """oracle/navdp_backward.py (explicit dgrad / wgrad / LayerNorm / GELU / softmax-attention backward, the spec of the
+    backward kernels) against autograd through the restated forward: loss, every parameter gradient, d loss / d latents."""
+    from oracle import gen_golden_training as G, navdp_backward as NB
+    b = G.make_batch(dict(G.CASE, seed=202))
+    args = (b["hs"], b["traj_images"], b["traj_depths"], b["traj_poses"], b["video_frame_num"], b["noise"], b["timesteps"])
+    loss_a, grads_a, dhs_a = O.s1_training_grads(sd, *args)
+    with torch.no_grad():
+        loss_m, grads_m, dhs_m = NB.s1_training_backward(sd, *args)
+    assert abs(float(loss_a) - float(loss_m)) < 1e-6 * max(1.0, abs(float(loss_a)))
+    assert sorted(grads_a) == sorted(grads_m), set(grads_a) ^ set(grads_m)
+    worst = ("", 0.0)
+    for k, ga in grads_a.items():
+        gm = grads_m[k].reshape(ga.shape)
+        rel = float((gm - ga).norm() / (ga.norm() + 1e-12))
+        if rel > worst[1]:
+            worst = (k, rel)
+        assert rel < 2e-3 or float((gm - ga).abs().max()) < 1e-8, (k, rel)
+    rel_h = float((dhs_m - dhs_a).norm() / dhs_a.norm())
+    print("worst parameter gradient rel err", worst, "latent gradient rel err", rel_h)
+    assert rel_h < 2e-3
