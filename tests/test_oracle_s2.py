@@ -317,3 +317,25 @@ def test_latent_query_gradient_vs_transformers():
     ref = torch.stack([emb.grad[b, t:t + cfg["n_query"]] for b, t in enumerate(t_s_pos)]).sum(0, keepdim=True)
     assert mine.shape == ref.shape == (1, cfg["n_query"], cfg["hidden"])
     assert torch.allclose(mine, ref, atol=2e-5, rtol=2e-3), (mine - ref).abs().max()
+
+
+def test_handwritten_latent_query_backward_matches_autograd():
+    """oracle/qwen_backward.py (backward restricted to the TRAJ rows against the per-layer K/V cache; no autograd)
+    equals autograd through the padded-batch forward."""
+    from oracle import qwen_backward as QB
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=10, vocab_rows=256)
+    rng = np.random.Generator(np.random.PCG64(41))
+    gpp = [[(1, 8, 12)], [(1, 4, 8), (1, 4, 4)], [(1, 4, 4)]]
+    prompts = [Q.make_prompt(rng, 4 + 5 * i, gs, 13 - 4 * i) for i, gs in enumerate(gpp)]
+    grids = [g for gs in gpp for g in gs]
+    torch.manual_seed(6)
+    px = torch.randn(sum(t * h * w for t, h, w in grids), 1176)
+    ids, mask, t_s_pos = collate(prompts)
+    G = torch.randn(len(prompts), cfg["n_query"], cfg["hidden"])
+    ref = Q.latent_query_grads(sd, cfg, ids, mask, px, grids, t_s_pos, G)
+    with torch.no_grad():
+        mine = QB.latent_query_backward(sd, cfg, ids, mask, px, grids, t_s_pos, G)
+    rel = float((mine - ref).norm() / ref.norm())
+    print("latent_queries gradient rel err (TRAJ-row backward vs autograd)", rel)
+    assert mine.shape == ref.shape and rel < 1e-4
