@@ -200,6 +200,29 @@ int n1_resize_f32(n1_resize_plan p, const void* src_f32, int n_frames, float mul
 int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds_host, double* weights_host,
                      int32_t* fixed_host, int32_t* ksize);
 
+/* ------------------------------------------------------------------------------------------------ training: backward primitives
+ * First version of the backward kernels of the training branch (internvla_n1.py L58-318; navdp.py L291-312), exposed
+ * one primitive at a time for parity tests against oracle/navdp_backward.py / oracle/qwen_backward.py.
+ * STATUS: compiled for sm_100a, not yet validated on a B200 (written after the round's GPU budget was spent); nothing on
+ * the inference path uses them.  All pointers are device pointers; activations bf16, parameter gradients fp32. */
+int n1_op_transpose(const void* in_bf16, int rows, int cols, int ld_in, void* out_bf16, int ld_out, int rows_pad, void* stream);
+int n1_op_colsum(const void* a_bf16, const void* b_bf16_or_null, int rows, int cols, int ld_a, int ld_b, void* out_f32,
+                 int accumulate, void* stream);
+int n1_op_norm_bwd(const void* dy_bf16, int ld_dy, const void* x_bf16, int ld_x, const void* w_f32, const void* residual_grad,
+                   int ld_rg, void* dx_bf16, int ld_dx, void* dw_f32, void* db_f32, int rows, int D, float eps, int rms,
+                   int accumulate, void* stream);
+int n1_op_act_bwd(const void* pre_bf16, const void* dy_bf16, void* out_bf16, int64_t n, int act, void* stream);
+int n1_op_swiglu_bwd(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, int64_t rows, int inter, void* stream);
+int n1_op_rope_transposed(void* x_bf16, int ld, const void* cos_sin_f32x2, int64_t rows, int heads, int head_dim, void* stream);
+/* same sequence description as n1_op_attention; o = forward output, dout its gradient; dk / dv fp32 [rows_k, heads_kv*hd],
+ * zeroed by the caller; for var-len K pass the maximum key length in seq_k */
+int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq, void* dk_f32,
+                        void* dv_f32, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int heads_q, int heads_kv,
+                        int head_dim, int batch, int seq_q, int seq_k, const void* cu_q, const void* cu_k, int max_seq_q,
+                        int kv_div, int causal, float scale, const void* k_len, int k_slot, void* stream);
+int n1_op_adamw(void* master_f32, void* working_bf16_or_null, const void* grad_f32, void* m_f32, void* v_f32, int64_t n,
+                float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ accounting
  * Kernel-launch counters are always on; with n1_prof_enable(1) every GEMM launch is additionally bracketed by CUDA
  * events on its stream (bench.py's roofline pass -- not for timed runs).  n1_prof_read synchronises, returns the sums

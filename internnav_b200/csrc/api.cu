@@ -6,6 +6,7 @@
 #include "../../include/n1b200.h"
 #include "n1_ops.h"
 #include "resize.h"
+#include "bwd_kernels.h"
 #include "s1_model.h"
 #include "s2_model.h"
 #include "weights.h"
@@ -375,6 +376,53 @@ int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds,
     memcpy(bounds, c.bounds.data(), c.bounds.size() * sizeof(int32_t));
     memcpy(weights, c.weights.data(), c.weights.size() * sizeof(double));
     memcpy(fixed, c.fixed.data(), c.fixed.size() * sizeof(int32_t));
+  });
+}
+
+int n1_op_transpose(const void* in, int rows, int cols, int ld_in, void* out, int ld_out, int rows_pad, void* stream) {
+  return guard([&] { transpose_bf16(B16(in), rows, cols, ld_in, B16(out), ld_out, rows_pad, S(stream)); });
+}
+int n1_op_colsum(const void* a, const void* b, int rows, int cols, int ld_a, int ld_b, void* out, int accumulate, void* stream) {
+  return guard([&] { colsum_bf16(B16(a), B16(b), rows, cols, ld_a, ld_b, static_cast<float*>(out), accumulate, S(stream)); });
+}
+int n1_op_norm_bwd(const void* dy, int ld_dy, const void* x, int ld_x, const void* w, const void* rg, int ld_rg, void* dx,
+                   int ld_dx, void* dw, void* db, int rows, int D, float eps, int rms, int accumulate, void* stream) {
+  return guard([&] {
+    norm_bwd(B16(dy), ld_dy, B16(x), ld_x, static_cast<const float*>(w), B16(rg), ld_rg, B16(dx), ld_dx,
+             static_cast<float*>(dw), static_cast<float*>(db), rows, D, eps, rms, accumulate, S(stream));
+  });
+}
+int n1_op_act_bwd(const void* pre, const void* dy, void* out, int64_t n, int act, void* stream) {
+  return guard([&] { act_bwd(B16(pre), B16(dy), B16(out), n, act, S(stream)); });
+}
+int n1_op_swiglu_bwd(const void* pre, const void* dact, void* dpre, int64_t rows, int inter, void* stream) {
+  return guard([&] { swiglu_bwd(B16(pre), B16(dact), B16(dpre), rows, inter, S(stream)); });
+}
+int n1_op_rope_transposed(void* x, int ld, const void* cs, int64_t rows, int heads, int head_dim, void* stream) {
+  return guard([&] { rope_transposed(B16(x), ld, static_cast<const float2*>(cs), rows, heads, head_dim, S(stream)); });
+}
+int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq, void* dk,
+                        void* dv, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int heads_q, int heads_kv, int hd,
+                        int batch, int seq_q, int seq_k, const void* cu_q, const void* cu_k, int max_seq_q, int kv_div,
+                        int causal, float scale, const void* k_len, int k_slot, void* stream) {
+  return guard([&] {
+    AttnBwdParams p = {};
+    p.f.q = B16(q), p.f.k = B16(k), p.f.v = B16(v), p.f.o = const_cast<bf16*>(B16(o));
+    p.f.ldq = ldq, p.f.ldk = ldk, p.f.ldv = ldv, p.f.ldo = ldo;
+    p.f.heads_q = heads_q, p.f.heads_kv = heads_kv, p.f.hd = hd, p.f.batch = batch, p.f.seq_q = seq_q, p.f.seq_k = seq_k;
+    p.f.cu_q = static_cast<const int*>(cu_q), p.f.cu_k = static_cast<const int*>(cu_k), p.f.max_seq_q = max_seq_q;
+    p.f.kv_div = kv_div, p.f.causal = causal, p.f.scale = scale;
+    p.f.k_len = static_cast<const int*>(k_len), p.f.k_slot = k_slot;
+    p.dout = B16(dout), p.lddo = lddo, p.dq = B16(dq), p.lddq = lddq;
+    p.dk = static_cast<float*>(dk), p.dv = static_cast<float*>(dv);
+    attention_bwd(p, S(stream));
+  });
+}
+int n1_op_adamw(void* master, void* working, const void* grad, void* m, void* v, int64_t n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int step, void* stream) {
+  return guard([&] {
+    adamw_step(static_cast<float*>(master), B16(working), static_cast<const float*>(grad), static_cast<float*>(m),
+               static_cast<float*>(v), n, lr, beta1, beta2, eps, weight_decay, step, S(stream));
   });
 }
 

@@ -75,3 +75,27 @@ def test_null_arguments_are_errors():
     assert L.n1_ddpm_tables(0, None) != 0
     assert L.n1_workspace_bytes(None, 1, 1, 1, 1) == 0 and b"null handle" in L.n1_last_error()
     L.n1_destroy(None)  # no-op
+
+
+def test_ctypes_signatures_have_the_declared_arity():
+    """Every ctypes binding in the package passes as many arguments as include/n1b200.h declares (a mismatch would
+    corrupt the call silently)."""
+    import re
+    from internnav_b200 import _bwd, _lib, preprocess, qwen
+    L = _lib.lib()
+    qwen._bind(L)
+    preprocess._bind(L)
+    _bwd._L()
+    with open(os.path.join(ROOT, "include", "n1b200.h")) as fh:
+        src = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(n1_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    checked = 0
+    for name, n in decl.items():
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, "%s: header declares %d arguments, binding passes %d" % (name, n, len(fn.argtypes))
+            checked += 1
+    assert checked >= 45, checked
