@@ -205,6 +205,15 @@ int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds_
  * one primitive at a time for parity tests against oracle/navdp_backward.py / oracle/qwen_backward.py.
  * STATUS: compiled for sm_100a, not yet validated on a B200 (written after the round's GPU budget was spent); nothing on
  * the inference path uses them.  All pointers are device pointers; activations bf16, parameter gradients fp32. */
+/* Training branch, System-2 half (internvla_n1.py L128-235 and its backward): `plan` is a generation plan over the
+ * prompts WITHOUT the TRAJ tokens (n1_gen_plan_create, max_new_tokens = 1).  Forward: states bf16 [B, n_query, hidden] =
+ * hidden states at the TRAJ positions.  Backward: grad_states bf16 [B, n_query, hidden] -> grad_latent_queries fp32
+ * [n_query, hidden].  Both calls must be given the SAME workspace (the forward leaves its K/V cache and saves there). */
+size_t n1_s2_train_workspace_bytes(n1_handle h, n1_llm_plan plan);
+int n1_s2_train_forward(n1_handle h, n1_llm_plan plan, void* ws, size_t ws_bytes, const void* image_feats_bf16,
+                        void* states_bf16, void* stream);
+int n1_s2_train_backward(n1_handle h, n1_llm_plan plan, void* ws, size_t ws_bytes, const void* grad_states_bf16,
+                         void* grad_latent_queries_f32, void* stream);
 int n1_op_transpose(const void* in_bf16, int rows, int cols, int ld_in, void* out_bf16, int ld_out, int rows_pad, void* stream);
 int n1_op_colsum(const void* a_bf16, const void* b_bf16_or_null, int rows, int cols, int ld_a, int ld_b, void* out_f32,
                  int accumulate, void* stream);

@@ -379,6 +379,30 @@ int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds,
   });
 }
 
+size_t n1_s2_train_workspace_bytes(n1_handle h, n1_llm_plan p) {
+  size_t r = 0;
+  guard([&] {
+    if (!h || !p) throw Error(N1_ERR_ARG, "null handle/plan");
+    r = h->s2.ws_train(*p->p);
+  });
+  return r;
+}
+int n1_s2_train_forward(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* image_feats, void* states,
+                        void* stream) {
+  return guard([&] {
+    use(h);
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    h->s2.train_forward(*p->p, ws, ws_bytes, B16(image_feats), B16(states), S(stream));
+  });
+}
+int n1_s2_train_backward(n1_handle h, n1_llm_plan p, void* ws, size_t ws_bytes, const void* grad_states, void* grad_latent,
+                         void* stream) {
+  return guard([&] {
+    use(h);
+    if (!p) throw Error(N1_ERR_ARG, "null plan");
+    h->s2.train_backward(*p->p, ws, ws_bytes, B16(grad_states), static_cast<float*>(grad_latent), S(stream));
+  });
+}
 int n1_op_transpose(const void* in, int rows, int cols, int ld_in, void* out, int ld_out, int rows_pad, void* stream) {
   return guard([&] { transpose_bf16(B16(in), rows, cols, ld_in, B16(out), ld_out, rows_pad, S(stream)); });
 }

@@ -81,6 +81,18 @@ class S2Model {
                     int32_t pad, GenResult& out, bf16* latents, cudaStream_t s) const;
   bool has_lm_head() const { return lm_head_.w != nullptr; }
 
+  // ---- training branch, System-2 half (s2_train.cu; STATUS: compiled, not yet validated on a B200)
+  // The decoder is frozen and causal: the TRAJ rows are a chunk appended to the prompt's K/V cache (exactly the latent
+  // pass of llm_generate), and d loss / d latent_queries needs the backward of those n_query rows per sample only
+  // (oracle/qwen_backward.py).  Both calls take a GENERATION plan over the prompts (without TRAJ tokens) and the SAME
+  // workspace: the forward leaves the cache and the per-layer TRAJ-row tensors there for the backward.
+  size_t ws_train(const LlmPlan& p) const;
+  // -> states bf16 [B, n_query, hidden] = hidden_states[b, t_s_pos[b] : t_s_pos[b] + n_query] (internvla_n1.py L231-235)
+  void train_forward(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, bf16* states, cudaStream_t s);
+  // grad_states bf16 [B, n_query, hidden] -> grad_latent fp32 [n_query, hidden] (summed over the batch)
+  void train_backward(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* grad_states, float* grad_latent,
+                      cudaStream_t s);
+
  private:
   struct KvCache {
     bf16 *k = nullptr, *v = nullptr;  // [layers][B * slot][kv_heads * head_dim]
@@ -114,6 +126,14 @@ class S2Model {
   std::vector<LBlock> lblk_;
   float* final_norm_ = nullptr;
   Lin lm_head_;  // optional ("lm_head.weight"); only generate() needs it
+  // transposed copies of the frozen decoder weights for the dgrad GEMMs of train_backward (built on first use)
+  struct LBlockT {
+    Lin qkv, o, gateup, down;
+  };
+  std::vector<LBlockT> lblk_t_;
+  struct TrainBufs;
+  size_t train_carve(Carver& c, const LlmPlan& p, TrainBufs& t) const;
+  void ensure_transposed(cudaStream_t s);
 };
 
 }  // namespace n1

@@ -85,6 +85,12 @@ def _bind(L):
     L.n1_llm_generate.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
                                   ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp,
                                   ctypes.POINTER(ctypes.c_int32), vp]
+    L.n1_s2_train_workspace_bytes.restype = ctypes.c_size_t
+    L.n1_s2_train_workspace_bytes.argtypes = [vp, vp]
+    L.n1_s2_train_forward.restype = ctypes.c_int
+    L.n1_s2_train_forward.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, vp, vp]
+    L.n1_s2_train_backward.restype = ctypes.c_int
+    L.n1_s2_train_backward.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, vp, vp]
     L._s2_bound = True
 
 
@@ -92,7 +98,7 @@ S2_SYMBOLS = ["n1_s2_load", "n1_vit_plan_create", "n1_vit_plan_destroy", "n1_vit
               "n1_llm_plan_destroy", "n1_llm_plan_tokens", "n1_llm_plan_image_tokens", "n1_llm_plan_positions",
               "n1_vit_workspace_bytes", "n1_llm_workspace_bytes", "n1_qwen_vit", "n1_llm_prefill", "n1_rope_index",
               "n1_vit_window_index", "n1_gen_plan_create", "n1_generate_workspace_bytes", "n1_s2_has_lm_head",
-              "n1_llm_generate"]
+              "n1_llm_generate", "n1_s2_train_workspace_bytes", "n1_s2_train_forward", "n1_s2_train_backward"]
 
 EOS_TOKEN_IDS = (151645, 151643)  # Qwen2.5-VL generation_config.json: <|im_end|>, <|endoftext|>
 PAD_TOKEN_ID = 151643
@@ -249,6 +255,30 @@ class System2:
     def generate_latents(self, prompts, pixel_values, grid_thw):
         """Batched InternVLAN1ForCausalLM.generate_latents: one prompt per environment, images in prompt order."""
         return self.prefill_latents(prompts, self.visual(pixel_values, grid_thw), grid_thw)
+
+    # ------------------------------------------------------------------ training branch (UNVALIDATED on GPU, see s2_train.cu)
+    def train_forward(self, prompts, pixel_values, grid_thw, image_feats=None):
+        """Hidden states at the TRAJ positions for a training batch (prompts WITHOUT the TRAJ tokens): [B, n_query, H].
+        Keeps the K/V cache and the per-layer TRAJ-row tensors for `train_backward` (same prompts, next call)."""
+        L = _lib.lib()
+        plan = self.gen_plan(prompts, grid_thw, 1)
+        feats = self.visual(pixel_values, grid_thw) if image_feats is None else image_feats
+        feats = feats.to(self.device, torch.bfloat16).contiguous()
+        out = torch.empty(len(prompts), self.cfg["n_query"], self.cfg["hidden"], device=self.device, dtype=torch.bfloat16)
+        nb = L.n1_s2_train_workspace_bytes(self._h(), plan)
+        ws = self._scratch("train", nb)
+        check(L.n1_s2_train_forward(self._h(), plan, _lib.ptr(ws), nb, _lib.ptr(feats), _lib.ptr(out), _lib.stream_ptr()))
+        self._train_state = (plan, ws, nb)
+        return out
+
+    def train_backward(self, grad_states):
+        """d loss / d traj states [B, n_query, H] -> d loss / d latent_queries fp32 [1, n_query, H]."""
+        plan, ws, nb = self._train_state
+        g = grad_states.to(self.device, torch.bfloat16).contiguous()
+        out = torch.empty(1, self.cfg["n_query"], self.cfg["hidden"], device=self.device, dtype=torch.float32)
+        check(_lib.lib().n1_s2_train_backward(self._h(), plan, _lib.ptr(ws), nb, _lib.ptr(g), _lib.ptr(out),
+                                              _lib.stream_ptr()))
+        return out
 
     def gen_plan(self, prompts, grid_thw, max_new_tokens):
         gkey = tuple(int(v) for g in grid_thw for v in g)

@@ -133,3 +133,35 @@ def test_adamw_matches_torch():
         K.adamw(master, work, g, m, v, 1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, step=step)
         assert _rel(master, ref.data) < 1e-6
         assert torch.equal(work, master.bfloat16())
+
+
+def test_s2_training_forward_and_latent_query_gradient():
+    """System-2 half of the training step on the GPU: TRAJ states and d loss / d latent_queries vs the oracle (padded-batch
+    forward + autograd), tiny config, ragged prompts."""
+    import numpy as np
+    from internnav_b200.qwen import System2
+    from oracle import qwen_oracle as Q
+    cfg = Q.tiny_cfg()
+    sd = Q.make_s2_state_dict(cfg, seed=10, vocab_rows=256)
+    s2 = System2(cfg, device="cuda:0")
+    s2.load_state_dict(sd)
+    rng = np.random.Generator(np.random.PCG64(41))
+    gpp = [[(1, 8, 12)], [(1, 4, 8), (1, 4, 4)], [(1, 4, 4)]]
+    prompts = [Q.make_prompt(rng, 4 + 5 * i, gs, 13 - 4 * i) for i, gs in enumerate(gpp)]
+    grids = [g for gs in gpp for g in gs]
+    px = torch.randn(sum(t * h * w for t, h, w in grids), 1176, generator=torch.Generator().manual_seed(6)).bfloat16()
+    G = torch.randn(len(prompts), cfg["n_query"], cfg["hidden"], generator=torch.Generator().manual_seed(7))
+    states = s2.train_forward(prompts, px.cuda(), grids)
+    grad = s2.train_backward(G.cuda())
+    rows = [list(p) + [Q.TRAJ_TOKEN_INDEX] * 4 for p in prompts]
+    S = max(len(r) for r in rows)
+    ids = torch.tensor([r + [151643] * (S - len(r)) for r in rows])
+    mask, t_s_pos = ids.ne(151643), [len(p) for p in prompts]
+    with torch.no_grad():
+        ref_states = Q.training_traj_states(sd, cfg, ids, mask, px.float(), grids, t_s_pos)
+    ref_grad = Q.latent_query_grads(sd, cfg, ids, mask, px.float(), grids, t_s_pos, G.bfloat16().float())
+    e_s, e_g = _rel(states.cpu(), ref_states), _rel(grad.cpu(), ref_grad)
+    print("S2 train: states rel err", e_s, "latent_queries grad rel err", e_g)
+    assert e_s < 2e-2 and e_g < 4e-2
+    # and the states equal the inference latent plan of the same prompts (same kernels, different chunking)
+    assert _rel(states, s2.generate_latents(prompts, px.cuda(), grids)) < 5e-3
