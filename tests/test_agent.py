@@ -108,3 +108,37 @@ def test_invalid_mode_and_missing_plan():
     ag.plans[0].actions = None
     with pytest.raises((AssertionError, IndexError)):
         ag.step([agent_script.make_obs(0)])
+
+
+def test_batched_agent_equals_oracle_on_random_scripts():
+    """Beyond the recorded traces: 60 random scripts (both modes, three System-2 budgets, random resets and failures),
+    batched agent with 5 environments per run vs five independent single-environment oracles -- the oracle being pinned to
+    the reference class by the traces above."""
+    from internnav_b200.agent import InternVLAN1Agent, PerEnvPolicies
+    rng = np.random.Generator(np.random.PCG64(2024))
+    for trial in range(12):
+        mode = "partial_async" if trial % 3 else "sync"
+        max_fwd = int(rng.choice([4, 8, 12]))
+        B, steps = 5, 45
+        scripts = [agent_script.random_script(rng, p_latent=float(rng.uniform(0.2, 0.9)), p_raise=float(rng.uniform(0, 0.12)))
+                   for _ in range(B)]
+        resets = {int(rng.integers(5, steps)): int(rng.integers(0, B)) for _ in range(2)}
+        pols_a = [agent_script.ScriptedPolicy(s) for s in scripts]
+        pols_b = [agent_script.ScriptedPolicy(s) for s in scripts]
+        ag = InternVLAN1Agent(PerEnvPolicies(pols_a), num_envs=B, infer_mode=mode, sys2_max_forward_step=max_fwd)
+        oracles = [AgentOracle(p, mode=mode, sys2_max_forward_step=max_fwd) for p in pols_b]
+        ag.reset()
+        for o in oracles:
+            o.reset()
+        for k in range(steps):
+            if k in resets:
+                ag.reset([resets[k]])
+                oracles[resets[k]].reset(reset_index=[0])
+            obs = [agent_script.make_obs(k + 3 * e) for e in range(B)]
+            out = ag.step(obs)
+            for e in range(B):
+                ref = oracles[e].step([obs[e]])
+                assert out[e]["action"] == ref[0]["action"], (trial, k, e)
+                assert _norm(pols_a[e].drain()) == _norm(pols_b[e].drain()), (trial, k, e)
+                assert int(ag.dual_forward_step[e]) == oracles[e].dual_forward_step
+                assert bool(ag.look_down[e]) == oracles[e].look_down
