@@ -220,6 +220,7 @@ int n1_op_colsum(const void* a_bf16, const void* b_bf16_or_null, int rows, int c
 int n1_op_norm_bwd(const void* dy_bf16, int ld_dy, const void* x_bf16, int ld_x, const void* w_f32, const void* residual_grad,
                    int ld_rg, void* dx_bf16, int ld_dx, void* dw_f32, void* db_f32, int rows, int D, float eps, int rms,
                    int accumulate, void* stream);
+int n1_op_act_fwd(const void* pre_bf16, void* out_bf16, int64_t n, int act, void* stream);
 int n1_op_act_bwd(const void* pre_bf16, const void* dy_bf16, void* out_bf16, int64_t n, int act, void* stream);
 int n1_op_swiglu_bwd(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, int64_t rows, int inter, void* stream);
 int n1_op_rope_transposed(void* x_bf16, int ld, const void* cos_sin_f32x2, int64_t rows, int heads, int head_dim, void* stream);

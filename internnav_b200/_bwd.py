@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 _bound = False
-BWD_SYMBOLS = ["n1_op_transpose", "n1_op_colsum", "n1_op_norm_bwd", "n1_op_act_bwd", "n1_op_swiglu_bwd",
+BWD_SYMBOLS = ["n1_op_act_fwd", "n1_op_transpose", "n1_op_colsum", "n1_op_norm_bwd", "n1_op_act_bwd", "n1_op_swiglu_bwd",
                "n1_op_rope_transposed", "n1_op_attention_bwd", "n1_op_adamw"]
 
 
@@ -25,6 +25,7 @@ def _L():
         L.n1_op_colsum.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, c_int, vp]
         L.n1_op_norm_bwd.argtypes = [vp, c_int, vp, c_int, vp, vp, c_int, vp, c_int, vp, vp, c_int, c_int, c_float, c_int,
                                      c_int, vp]
+        L.n1_op_act_fwd.argtypes = [vp, vp, c_int64, c_int, vp]
         L.n1_op_act_bwd.argtypes = [vp, vp, vp, c_int64, c_int, vp]
         L.n1_op_swiglu_bwd.argtypes = [vp, vp, vp, c_int64, c_int, vp]
         L.n1_op_rope_transposed.argtypes = [vp, c_int, vp, c_int64, c_int, c_int, vp]
@@ -63,6 +64,12 @@ def norm_bwd(dy, x, w, eps, rms=False, residual_grad=None, need_param_grads=True
                               residual_grad.stride(0) if residual_grad is not None else 0, ptr(dx), dx.stride(0), ptr(dw),
                               ptr(db), rows, D, eps, 1 if rms else 0, 0, stream_ptr()))
     return dx, dw, db
+
+
+def act_fwd(pre, act):
+    out = torch.empty_like(pre)
+    check(_L().n1_op_act_fwd(ptr(pre), ptr(out), pre.numel(), act, stream_ptr()))
+    return out
 
 
 def act_bwd(pre, dy, act):

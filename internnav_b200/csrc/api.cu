@@ -416,6 +416,9 @@ int n1_op_norm_bwd(const void* dy, int ld_dy, const void* x, int ld_x, const voi
              static_cast<float*>(dw), static_cast<float*>(db), rows, D, eps, rms, accumulate, S(stream));
   });
 }
+int n1_op_act_fwd(const void* pre, void* out, int64_t n, int act, void* stream) {
+  return guard([&] { act_fwd(B16(pre), B16(out), n, act, S(stream)); });
+}
 int n1_op_act_bwd(const void* pre, const void* dy, void* out, int64_t n, int act, void* stream) {
   return guard([&] { act_bwd(B16(pre), B16(dy), B16(out), n, act, S(stream)); });
 }

@@ -127,6 +127,13 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ pre, const bf16* __restr
   out[i] = __float2bfloat16(g * d);
 }
 
+__global__ void act_fwd_kernel(const bf16* __restrict__ pre, bf16* __restrict__ out, long n, int kind) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = ldf(pre + i);
+  out[i] = __float2bfloat16(kind == ACT_GELU ? 0.5f * x * (1.f + erff(x * 0.70710678118654752f)) : fmaxf(x, 0.f));
+}
+
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dact, bf16* __restrict__ dpre,
                                   long n) {  // n = rows * inter
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,6 +351,12 @@ void norm_bwd(const bf16* dy, int ld_dy, const bf16* x, int ld_x, const float* w
   }
 }
 
+void act_fwd(const bf16* pre, bf16* out, long n, int kind, cudaStream_t s) {
+  N1_CHECK(kind == ACT_GELU || kind == ACT_RELU, "act_fwd: GELU or ReLU");
+  act_fwd_kernel<<<nblk(n), 256, 0, s>>>(pre, out, n, kind);
+  prof_count_launch();
+  N1_CUDA(cudaGetLastError());
+}
 void act_bwd(const bf16* pre, const bf16* dy, bf16* out, long n, int kind, cudaStream_t s) {
   N1_CHECK(kind == ACT_GELU || kind == ACT_RELU, "act_bwd: GELU or ReLU");
   act_bwd_kernel<<<nblk(n), 256, 0, s>>>(pre, dy, out, n, kind);

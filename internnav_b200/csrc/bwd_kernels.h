@@ -26,6 +26,8 @@ void norm_bwd(const bf16* dy, int ld_dy, const bf16* x, int ld_x, const float* w
               bf16* dx, int ld_dx, float* dw, float* db, int rows, int D, float eps, int rms, int accumulate,
               cudaStream_t s);
 
+// Elementwise activation forward (training keeps the pre-activation, so the GEMM epilogue cannot fuse it): out = f(pre)
+void act_fwd(const bf16* pre, bf16* out, long n, int kind, cudaStream_t s);
 // Elementwise activation backward on the saved pre-activation: out = dy * f'(pre); kind: ACT_GELU (exact erf) / ACT_RELU
 void act_bwd(const bf16* pre, const bf16* dy, bf16* out, long n, int kind, cudaStream_t s);
 // SwiGLU backward: pre [R, 2I] interleaved (gate_j, up_j) pre-activations, dact [R, I] -> dpre [R, 2I] interleaved
