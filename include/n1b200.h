@@ -205,10 +205,15 @@ int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds_
  * one primitive at a time for parity tests against oracle/navdp_backward.py / oracle/qwen_backward.py.
  * STATUS: compiled for sm_100a, not yet validated on a B200 (written after the round's GPU budget was spent); nothing on
  * the inference path uses them.  All pointers are device pointers; activations bf16, parameter gradients fp32. */
+/* Training branch, System-1 side: tokens of the frozen RGB ViT (final norm, cls dropped, former_pe added) written into
+ * the first frames*256 rows of every environment of mem bf16 [B, 2*frames*256, 384]; rgb fp32 [B, frames, 224, 224, 3]. */
+size_t n1_rgb_tokens_workspace_bytes(n1_handle h, int B);
+int n1_rgb_tokens(n1_handle h, void* ws, size_t ws_bytes, const float* rgb, void* mem_bf16, int B, void* stream);
 /* Training branch, System-2 half (internvla_n1.py L128-235 and its backward): `plan` is a generation plan over the
  * prompts WITHOUT the TRAJ tokens (n1_gen_plan_create, max_new_tokens = 1).  Forward: states bf16 [B, n_query, hidden] =
  * hidden states at the TRAJ positions.  Backward: grad_states bf16 [B, n_query, hidden] -> grad_latent_queries fp32
  * [n_query, hidden].  Both calls must be given the SAME workspace (the forward leaves its K/V cache and saves there). */
+int n1_s2_set_latent_queries(n1_handle h, const void* latent_queries_bf16, void* stream);  /* after an optimizer step */
 size_t n1_s2_train_workspace_bytes(n1_handle h, n1_llm_plan plan);
 int n1_s2_train_forward(n1_handle h, n1_llm_plan plan, void* ws, size_t ws_bytes, const void* image_feats_bf16,
                         void* states_bf16, void* stream);

@@ -379,6 +379,26 @@ int n1_resize_coeffs(int in_size, int out_size, int capacity_k, int32_t* bounds,
   });
 }
 
+size_t n1_rgb_tokens_workspace_bytes(n1_handle h, int B) {
+  size_t r = 0;
+  guard([&] {
+    if (!h || B <= 0) throw Error(N1_ERR_ARG, "null handle / B <= 0");
+    r = h->s1.ws_rgb_tokens(B);
+  });
+  return r;
+}
+int n1_rgb_tokens(n1_handle h, void* ws, size_t ws_bytes, const float* rgb, void* mem, int B, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.rgb_tokens(ws, ws_bytes, rgb, B16(mem), B, S(stream));
+  });
+}
+int n1_s2_set_latent_queries(n1_handle h, const void* src, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s2.set_latent_queries(B16(src), S(stream));
+  });
+}
 size_t n1_s2_train_workspace_bytes(n1_handle h, n1_llm_plan p) {
   size_t r = 0;
   guard([&] {

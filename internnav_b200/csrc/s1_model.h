@@ -62,6 +62,11 @@ class S1Model {
   size_t ws_rgbd(int B) const;
   void rgbd_encode(void* ws, size_t ws_bytes, const float* rgb, const float* depth, bf16* out, int B,
                    cudaStream_t s) const;
+  // Training branch (s1_train.cu; compiled, not yet validated on a B200): the tokens of the FROZEN RGB ViT for the
+  // [goal frame, current frame] pairs, as the Q-former sees them -- final LayerNorm, cls dropped, former_pe added --
+  // mem bf16 [B, 2 * frames * 256, D]: only the first frames * 256 rows of every environment are written.
+  size_t ws_rgb_tokens(int B) const;
+  void rgb_tokens(void* ws, size_t ws_bytes, const float* rgb, bf16* mem, int B, cudaStream_t s) const;
   // latents bf16 [B, n_query, vlm_dim] -> goal bf16 [B, 1, D]
   size_t ws_goal(int B) const;
   void goal_compress(void* ws, size_t ws_bytes, const bf16* latents, bf16* goal, int B, cudaStream_t s) const;

@@ -86,6 +86,8 @@ class S2Model {
   // pass of llm_generate), and d loss / d latent_queries needs the backward of those n_query rows per sample only
   // (oracle/qwen_backward.py).  Both calls take a GENERATION plan over the prompts (without TRAJ tokens) and the SAME
   // workspace: the forward leaves the cache and the per-layer TRAJ-row tensors there for the backward.
+  // overwrite the library's copy of `latent_queries` (bf16 [n_query, hidden], device) after an optimizer step
+  void set_latent_queries(const bf16* src, cudaStream_t s);
   size_t ws_train(const LlmPlan& p) const;
   // -> states bf16 [B, n_query, hidden] = hidden_states[b, t_s_pos[b] : t_s_pos[b] + n_query] (internvla_n1.py L231-235)
   void train_forward(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* image_feats, bf16* states, cudaStream_t s);

@@ -101,6 +101,11 @@ size_t S2Model::train_carve(Carver& c, const LlmPlan& p, TrainBufs& t) const {
   return c.used();
 }
 
+void S2Model::set_latent_queries(const bf16* src, cudaStream_t s) {
+  N1_CHECK(loaded_ && src, "set_latent_queries: not loaded / null source");
+  N1_CUDA(cudaMemcpyAsync(latentq_, src, (size_t)dims.n_query * dims.hidden * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+}
+
 size_t S2Model::ws_train(const LlmPlan& p) const {
   N1_CHECK(p.max_new > 0, "ws_train: needs a generation plan (prompts without TRAJ tokens)");
   Carver c(nullptr, 0);

@@ -141,6 +141,21 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
                                        _lib.stream_ptr()))
         return out
 
+    def rgb_memory_tokens(self, images):
+        """Training branch: tokens of the frozen RGB ViT as the Q-former sees them (final norm, cls dropped, former_pe
+        added): images [B, frames, 224, 224, 3] -> bf16 [B, frames * 256, D].  (UNVALIDATED on GPU, see s1_train.cu.)"""
+        B = images.shape[0]
+        want = (self.memory_size, self.image_size, self.image_size, 3)
+        if tuple(images.shape[1:]) != want:
+            raise ValueError("rgb_memory_tokens takes images [B, %d, %d, %d, 3]; got %s" % (want[:3] + (tuple(images.shape),)))
+        rgb = images.to(self._device, torch.float32).contiguous()
+        mem = torch.zeros(B, 2 * self.memory_size * 256, self.token_dim, device=self._device, dtype=torch.bfloat16)
+        L = _lib.lib()
+        nb = L.n1_rgb_tokens_workspace_bytes(self._h(), B)
+        ws = torch.empty(int(nb) + 256, dtype=torch.uint8, device=self._device)
+        check(L.n1_rgb_tokens(self._h(), _lib.ptr(ws), nb, _lib.ptr(rgb), _lib.ptr(mem), B, _lib.stream_ptr()))
+        return mem[:, : self.memory_size * 256]
+
     def goal_embed(self, vlm_tokens):
         """vlm_embed_mlp + goal_compressor (navdp.py L237-238): [B, n_query, 3584] -> [B, 1, 384]."""
         B = vlm_tokens.shape[0]

@@ -85,6 +85,8 @@ def _bind(L):
     L.n1_llm_generate.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
                                   ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp,
                                   ctypes.POINTER(ctypes.c_int32), vp]
+    L.n1_s2_set_latent_queries.restype = ctypes.c_int
+    L.n1_s2_set_latent_queries.argtypes = [vp, vp, vp]
     L.n1_s2_train_workspace_bytes.restype = ctypes.c_size_t
     L.n1_s2_train_workspace_bytes.argtypes = [vp, vp]
     L.n1_s2_train_forward.restype = ctypes.c_int
@@ -98,7 +100,7 @@ S2_SYMBOLS = ["n1_s2_load", "n1_vit_plan_create", "n1_vit_plan_destroy", "n1_vit
               "n1_llm_plan_destroy", "n1_llm_plan_tokens", "n1_llm_plan_image_tokens", "n1_llm_plan_positions",
               "n1_vit_workspace_bytes", "n1_llm_workspace_bytes", "n1_qwen_vit", "n1_llm_prefill", "n1_rope_index",
               "n1_vit_window_index", "n1_gen_plan_create", "n1_generate_workspace_bytes", "n1_s2_has_lm_head",
-              "n1_llm_generate", "n1_s2_train_workspace_bytes", "n1_s2_train_forward", "n1_s2_train_backward"]
+              "n1_llm_generate", "n1_s2_train_workspace_bytes", "n1_s2_train_forward", "n1_s2_train_backward", "n1_s2_set_latent_queries"]
 
 EOS_TOKEN_IDS = (151645, 151643)  # Qwen2.5-VL generation_config.json: <|im_end|>, <|endoftext|>
 PAD_TOKEN_ID = 151643
@@ -270,6 +272,12 @@ class System2:
         check(L.n1_s2_train_forward(self._h(), plan, _lib.ptr(ws), nb, _lib.ptr(feats), _lib.ptr(out), _lib.stream_ptr()))
         self._train_state = (plan, ws, nb)
         return out
+
+    def set_latent_queries(self, latent_queries):
+        """Push updated `latent_queries` ([1, n_query, H] or [n_query, H]) into the library after an optimizer step."""
+        t = latent_queries.reshape(self.cfg["n_query"], self.cfg["hidden"]).to(self.device, torch.bfloat16).contiguous()
+        check(_lib.lib().n1_s2_set_latent_queries(self._h(), _lib.ptr(t), _lib.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
 
     def train_backward(self, grad_states):
         """d loss / d traj states [B, n_query, H] -> d loss / d latent_queries fp32 [1, n_query, H]."""

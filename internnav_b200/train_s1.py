@@ -282,14 +282,16 @@ class S1TrainStep:
         return ops.cast(d.float() + dq.float()), dmem
 
     # ---- model pieces ------------------------------------------------------------------------------------------
-    def rgbd_fwd(self, rgb_tokens, depths):
-        """rgb_tokens: [B, T*256, D] from the frozen RGB ViT (detached in the reference, navdp_backbone.py L170-171;
-        the inference kernel n1_rgbd_encode's ViT is reused for it by the caller); depths [B, T, 224, 224, 1]."""
+    def rgbd_fwd(self, rgb_tokens, depths, rgb_has_pe=False):
+        """rgb_tokens: [B, T*256, D] from the frozen RGB ViT (detached in the reference, navdp_backbone.py L170-171);
+        `rgb_has_pe`: they already carry former_pe (n1_rgb_tokens delivers them that way); depths [B, T, 224, 224, 1]."""
         ops, p = self.ops, "rgbd_encoder."
         B, T = depths.shape[:2]
         td = depths.permute(0, 1, 4, 2, 3).reshape(-1, 1, 224, 224)
         dtok, vsave = self.vit_fwd(p + "depth_model.", torch.cat([td, td, td], dim=1))
-        pe = self._f32(p + "former_pe.weight")[: self.frames * 512]
+        pe = self._f32(p + "former_pe.weight")[: self.frames * 512].clone()
+        if rgb_has_pe:
+            pe[: T * 256] = 0
         token = ops.cast(torch.cat((rgb_tokens.float(), dtok.reshape(B, T * 256, -1).float()), dim=1) + pe)
         x = ops.cast(self._f32(p + "former_query.weight")[: self.frames * 16].unsqueeze(0).expand(B, -1, -1))
         tape = []
@@ -415,7 +417,7 @@ class S1TrainStep:
 
     # ---- the step ----------------------------------------------------------------------------------------------
     def forward_backward(self, traj_hidden_states, rgb_tokens, traj_depths, traj_poses, video_frame_num, noise, timesteps,
-                         alphas_cumprod):
+                         alphas_cumprod, rgb_has_pe=False):
         """-> (loss, {name: fp32 gradient}, d loss / d traj_hidden_states [B, n_query, H]).
         rgb_tokens: [B*f, 2*256, D] RGB-ViT tokens of the [goal frame, current frame] pairs (frozen branch);
         traj_depths [B, f, 224, 224]; alphas_cumprod fp32 [K] (DDPMScheduler table, n1_ddpm_tables)."""
@@ -431,7 +433,7 @@ class S1TrainStep:
         acp = alphas_cumprod.to(dev)[timesteps]
         noisy = acp.sqrt()[:, None, None] * poses + (1 - acp).sqrt()[:, None, None] * noise       # add_noise, navdp.py L173
         goal, gsave = self.goal_fwd(hs)
-        rgbd, rsave = self.rgbd_fwd(rgb_tokens.to(dev), depths_dp)
+        rgbd, rsave = self.rgbd_fwd(rgb_tokens.to(dev), depths_dp, rgb_has_pe)
         pred, dsave = self.decoder_fwd(noisy, timesteps, goal, rgbd)
         err = pred - noise
         denom = mask.sum() * err.shape[1] * err.shape[2]

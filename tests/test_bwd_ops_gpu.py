@@ -165,3 +165,57 @@ def test_s2_training_forward_and_latent_query_gradient():
     assert e_s < 2e-2 and e_g < 4e-2
     # and the states equal the inference latent plan of the same prompts (same kernels, different chunking)
     assert _rel(states, s2.generate_latents(prompts, px.cuda(), grids)) < 5e-3
+
+
+def test_dual_system_training_step_vs_oracle():
+    """End to end on the GPU: collated batch -> S2 TRAJ states -> S1 forward / backward -> latent_queries gradient, against
+    the oracle chain (padded-batch decoder + autograd through the restated System 1); then one AdamW step moves the
+    masters in the direction torch.optim.AdamW moves them."""
+    import numpy as np
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from internnav_b200.manifest import random_navdp_state_dict
+    from internnav_b200.train_step import DualSystemTrainer
+    from internnav_b200.training import collate_traj_batch
+    from oracle import navdp_oracle as O, qwen_oracle as Q
+    cfg = Q.tiny_cfg()
+    s2_sd = Q.make_s2_state_dict(cfg, seed=31, vocab_rows=512)
+    s1_sd = {k: v.float() for k, v in random_navdp_state_dict(seed=32, vlm_token_dim=cfg["hidden"]).items()}
+    model = InternVLAN1ForCausalLM(cfg, device="cuda:0")
+    model.load_parts(s2_sd, s1_sd)
+    rng = np.random.Generator(np.random.PCG64(33))
+    g = torch.Generator().manual_seed(34)
+    gpp, frames = [[(1, 8, 12)], [(1, 4, 8)]], [2, 1]
+    inst = []
+    for gs, f in zip(gpp, frames):
+        ids = torch.tensor([Q.make_prompt(rng, 6, gs, 11)])
+        n_p = sum(t * h * w for t, h, w in gs)
+        inst.append(dict(input_ids=ids, labels=torch.full_like(ids, -100), pixel_values=torch.randn(n_p, 1176, generator=g).bfloat16(),
+                         image_grid_thw=torch.tensor(gs), traj_images=torch.rand(f, 224, 224, 3, generator=g),
+                         traj_depths=torch.rand(f, 224, 224, generator=g) * 5, traj_poses=torch.randn(f, 32, 3, generator=g) * 0.5))
+    batch = collate_traj_batch(inst)
+    B, fmax = len(inst), max(frames)
+    noise = torch.randn(B * fmax, 32, 3, generator=g)
+    ts = torch.randint(0, 20, (B * fmax,), generator=g)
+    tr = DualSystemTrainer(model, s1_sd, s2_sd["model.latent_queries"], lr=1e-3)
+    loss, grads, hs = tr.loss_and_grads(batch, noise, ts)
+    # oracle chain on the CPU (fp32)
+    with torch.no_grad():
+        hs_ref = Q.training_traj_states(s2_sd, cfg, batch["input_ids"], batch["attention_mask"], batch["pixel_values"].float(),
+                                        batch["image_grid_thw"], batch["t_s_pos"])
+    loss_ref, grads_ref, dhs_ref = O.s1_training_grads(s1_sd, hs_ref, batch["traj_images"], batch["traj_depths"],
+                                                       batch["traj_poses"], batch["video_frame_num"], noise, ts)
+    glat_ref = Q.latent_query_grads(s2_sd, cfg, batch["input_ids"], batch["attention_mask"], batch["pixel_values"].float(),
+                                    batch["image_grid_thw"], batch["t_s_pos"], dhs_ref)
+    print("train step: loss", float(loss), "oracle", float(loss_ref), "TRAJ states rel", _rel(hs.cpu(), hs_ref))
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 3e-2
+    bad = []
+    for k, gr in grads_ref.items():
+        rel = _rel(grads[k].cpu().reshape(gr.shape), gr)
+        if rel > 0.08 and float(gr.norm()) > 1e-6:
+            bad.append((k, rel))
+    print("parameter gradients beyond 8 %:", bad[:10], "of", len(grads_ref))
+    assert len(bad) <= len(grads_ref) // 50
+    assert _rel(grads["model.latent_queries"].cpu(), glat_ref) < 0.1
+    before = {k: v.clone() for k, v in list(tr.masters.items())[:5]}
+    tr.step(batch, noise, ts)
+    assert tr.steps == 1 and any(not torch.equal(before[k], tr.masters[k]) for k in before if k in tr.buckets.grads)
