@@ -88,6 +88,8 @@ class DualSystemTrainer:
         self.steps += 1
         o = self.opt
         for k, g in self.buckets.grads.items():
+            if k not in grads:   # torch.optim skips parameters whose .grad is None (no update, no weight decay)
+                continue
             master = self.latent if k == "model.latent_queries" else self.masters[k]
             _bwd.adamw(master.view(-1), None, g.view(-1), self.m[k].view(-1), self.v[k].view(-1), o["lr"], betas=o["betas"],
                        eps=o["eps"], weight_decay=o["weight_decay"], step=self.steps)
