@@ -96,7 +96,10 @@ def attention_bwd(q, k, v, o, dout, heads_q, heads_kv, head_dim, batch, seq_q, s
     dk = torch.zeros(k.shape[0], heads_kv * head_dim, dtype=torch.float32, device=q.device)
     dv = torch.zeros_like(dk)
     scale = head_dim ** -0.5 if scale is None else scale
-    check(_L().n1_op_attention_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(dq), ptr(dk), ptr(dv), q.stride(0),
+    for t in (q, k, v, o, dout):   # column slices of packed projections are legal operands: row stride + unit inner stride
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
+    vp = lambda t: c_void_p(t.data_ptr())
+    check(_L().n1_op_attention_bwd(vp(q), vp(k), vp(v), vp(o), vp(dout), ptr(dq), ptr(dk), ptr(dv), q.stride(0),
                                    k.stride(0), v.stride(0), o.stride(0), dout.stride(0), dq.stride(0), heads_q, heads_kv,
                                    head_dim, batch, seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div,
                                    1 if causal else 0, scale, ptr(k_len), k_slot, stream_ptr()))

@@ -115,6 +115,11 @@ def test_attention_bwd(B, Sq, Sk, Hq, Hkv, hd, causal):
     o = L.attention(q, k, v, Hq, Hkv, hd, B, Sq, Sk, causal=causal)
     dq, dk, dv = K.attention_bwd(q, k, v, o, do, Hq, Hkv, hd, B, Sq, Sk, causal=causal)
     assert _rel(dq, qf.grad) < 1.5e-2 and _rel(dk, kf.grad) < 1.5e-2 and _rel(dv, vf.grad) < 1.5e-2
+    if Sq == Sk and Hq == Hkv:   # column slices of one packed [rows, 3D] projection, as the training schedule passes them
+        D = Hq * hd
+        qkv = torch.cat((q, k, v), dim=1)
+        dq2, dk2, dv2 = K.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, Hq, Hkv, hd, B, Sq, Sk, causal=causal)
+        assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
 def test_adamw_matches_torch():
