@@ -35,6 +35,16 @@ WORKLOADS = {
                         desc="configs[3]: full dual-system step (Qwen2.5-VL-7B ViT + LLM prefill -> 4 latents -> NavDP "
                              "RGB-D encoder + 20-step DDPM, 32 samples, horizon 32 -> action ids), 64 parallel envs, bf16; "
                              "per env one 392x392 frame (784 patches -> 196 tokens) + 104 text tokens + 4 latent queries = 304"),
+    "s2_prefill": dict(kind="s2", B=32, S=304, grid=(1, 28, 28),
+                       desc="configs[2]: System-2 VLM forward only (Qwen2.5-VL-7B ViT + LLM prefill -> 4 latent tokens), "
+                            "32 frames (392x392 -> 784 patches -> 196 tokens) x 80-token instruction + 24 template tokens + "
+                            "4 latent queries = 304 tokens per env, bf16"),
+    "ddp_train": dict(kind="train", B=32, f=6, S=304, grid=(1, 28, 28), T=32, K=20, Ns=1,
+                      desc="configs[4]: InternVLA-N1 DDP training step (navdp_async branch), 32 episodes per GPU (global "
+                           "batch 256 on 8 GPUs), S = 304 tokens (1 frame 392x392 + 104 text + 4 TRAJ), f = 6 selected "
+                           "frames per episode (192 [goal, current] RGB-D pairs), frozen 7B System 2, trainable System 1 + "
+                           "latent_queries, bucketed NCCL all-reduce of 76.8 M fp32 gradients overlapped with the System-2 "
+                           "backward, fused AdamW; dropout off (see train_step.py)"),
 }
 
 
@@ -168,10 +178,15 @@ def build_dual(dev, wl, rank):
 def run_ours(args, wl):
     if wl["kind"] == "dual":
         return run_ours_dual(args, wl)
+    if wl["kind"] == "s2":
+        return run_ours_s2(args, wl)
+    if wl["kind"] == "train":
+        return run_ours_train(args, wl)
     return run_ours_denoise(args, wl)
 
 
-def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, extra_cfg, e2e_info, algo_flops_step):
+def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, extra_cfg, e2e_info, algo_flops_step,
+            unit="policy-steps/s", metric="InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", extra_top=None):
     import torch.distributed as dist
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -187,10 +202,10 @@ def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, e
            "l2": "flushed (256 MiB memset) between timed steps", "algorithmic_tflop_per_step": algo_flops_step / 1e12,
            "step_tflops_achieved": algo_flops_step / (ms_per_step * 1e-3) / 1e12}
     cfg.update(extra_cfg)
-    e2e = {"value": e2e_value, "unit": "policy-steps/s"}
+    e2e = {"value": e2e_value, "unit": unit}
     e2e.update(e2e_info)
     out = {
-        "metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": value, "unit": "policy-steps/s",
+        "metric": metric, "value": value, "unit": unit,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, MIN_WARMUP), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "impl": "ours", "config": cfg, "e2e": e2e, "gpu_launches": int(launches["total_launches"]), "clocks": clocks,
@@ -200,8 +215,10 @@ def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, e
                      "gemm_launches_per_step": int(prof["gemm_launches"]), "gemm_ms_per_step": prof["gemm_ms"],
                      "gemm_share_of_step": prof["gemm_ms"] / ms_per_step},
     }
+    if extra_top:
+        out.update(extra_top)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wl["kind"] in ("dual", "denoise"):
             out["cpu_baseline"] = cpu_baseline(wl, budget_s=20.0)
         emit(out)
     if world > 1:
@@ -254,14 +271,22 @@ def run_ours_dual(args, wl):
     B = wl["B"]
     d = {k: v.to(dev) for k, v in host.items()}
     barrier, timed = _timing_tools(dev, world)
+    # deployment never sees the same prompts twice: 32 rotating prompt batches (the plan cache holds 8), so every step --
+    # timed or not -- builds its integer plan (mRoPE ids, splice map, cu_seqlens, RoPE table) inside the step
+    sets = _prompt_sets(wl, rank, 32)
+    it = [0]
+
+    def next_prompts():
+        it[0] += 1
+        return sets[it[0] % len(sets)]
 
     def step_resident():
-        lat = model.generate_latents(prompts, d["pixels"], grids)
+        lat = model.generate_latents(next_prompts(), d["pixels"], grids)
         return model.generate_traj(lat, d["rgb"], d["depth"], x_init=d["x0"], step_noise=d["nz"])
 
     def step_e2e():
         h2d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return model.dual_system_step(prompts, h2d["pixels"], grids, h2d["rgb"], h2d["depth"], x_init=h2d["x0"],
+        return model.dual_system_step(next_prompts(), h2d["pixels"], grids, h2d["rgb"], h2d["depth"], x_init=h2d["x0"],
                                       step_noise=h2d["nz"])[1]
 
     for _ in range(max(args.warmup, MIN_WARMUP)):
@@ -288,11 +313,221 @@ def run_ours_dual(args, wl):
     _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
             {"seq_len": wl["S"], "patches_per_env": wl["grid"][1] * wl["grid"][2], "samples_per_env": wl["Ns"],
              "horizon": wl["T"], "ddpm_steps": wl["K"], "weights": "random-init Qwen2.5-VL-7B shapes + NavDP (bf16)",
-             "tflop_per_env": {k: v / 1e12 for k, v in fl.items()}, "launches_are": "per step"},
+             "tflop_per_env": {k: v / 1e12 for k, v in fl.items()}, "launches_are": "per step",
+             "prompts": "a different prompt batch every step (32 rotating sets, plan cache of 8): plan creation is inside "
+                        "the timed region of both `value` and `e2e`"},
             {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host.values()),
              "d2h_bytes_per_step": B * wl["Ns"] * wl["T"] * 3 * 4,
              "api": "InternVLAN1ForCausalLM.dual_system_step (generate_latents + generate_traj + traj_to_actions), pinned host inputs"},
             fl["total"] * B)
+
+
+def _prompt_sets(wl, rank, n_sets):
+    """`n_sets` different prompt batches (fresh instruction tokens): deployment never sees the same prompts twice, so the
+    integer plan (mRoPE ids, splice map, cu_seqlens) is rebuilt inside every timed step."""
+    import numpy as np
+    B, S = wl["B"], wl["S"]
+    t, h, w = wl["grid"]
+    n_tok = t * h * w // 4
+    n_text = S - 4 - n_tok - 2
+    sets = []
+    for k in range(n_sets):
+        rng = np.random.Generator(np.random.PCG64([77 + rank, k]))
+        prompts = []
+        for _ in range(B):
+            pre = rng.integers(0, 151643, 12).tolist()
+            post = rng.integers(0, 151643, n_text - 12).tolist()
+            prompts.append(pre + [151652] + [151655] * n_tok + [151653] + post)
+        sets.append(prompts)
+    return sets
+
+
+def run_ours_s2(args, wl):
+    """configs[2]: System-2 forward only (ViT + LLM prefill -> latents)."""
+    import torch.distributed as dist
+    from internnav_b200 import _lib
+    from internnav_b200.manifest import random_s2_state_dict
+    from internnav_b200.qwen import QWEN25VL_7B, System2
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    s2 = System2(QWEN25VL_7B, device=str(dev))
+    s2.load_state_dict(random_s2_state_dict(QWEN25VL_7B, seed=0, device=str(dev)))
+    torch.cuda.empty_cache()
+    B = wl["B"]
+    t, h, w = wl["grid"]
+    sets = _prompt_sets(wl, rank, 8)
+    grids = [list(wl["grid"])] * B
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    h_px = torch.randn(B * t * h * w, 1176, generator=g).bfloat16().pin_memory()
+    d_px = h_px.to(dev)
+    barrier, timed = _timing_tools(dev, world)
+    it = [0]
+
+    def step_resident():
+        it[0] += 1
+        return s2.generate_latents(sets[it[0] % len(sets)], d_px, grids)
+
+    def step_e2e():
+        it[0] += 1
+        return s2.generate_latents(sets[it[0] % len(sets)], h_px.to(dev, non_blocking=True), grids).float().cpu()
+
+    for _ in range(max(args.warmup, MIN_WARMUP)):
+        step_resident()
+    _lib.prof_read()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    barrier()
+    launches = _lib.prof_read()
+    launches["total_launches"] //= max(args.steps, 1)
+    clocks = clk.summary()
+    step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps, use_events=False)
+    barrier()
+    _lib.prof_read()
+    _lib.prof_enable(True)
+    step_resident()
+    torch.cuda.synchronize()
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    fl = dual_flops_per_env(dict(wl, T=32, Ns=32, K=20))
+    _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
+            {"seq_len": wl["S"], "patches_per_env": h * w, "weights": "random-init Qwen2.5-VL-7B shapes (bf16)",
+             "prompts": "a different prompt batch every step (8 rotating sets): plan creation is inside the timed region",
+             "tflop_per_env": {"llm": fl["llm"] / 1e12, "vit": fl["vit"] / 1e12}, "launches_are": "per step"},
+            {"h2d_bytes_per_step": h_px.numel() * 2, "d2h_bytes_per_step": B * 4 * 3584 * 4,
+             "api": "System2.generate_latents (= InternVLAN1ForCausalLM.generate_latents), pinned host pixel_values"},
+            (fl["llm"] + fl["vit"]) * B, unit="frames/s",
+            metric="InternVLA-N1 System-2 forward (ViT + LLM prefill -> latents), frames/sec")
+
+
+def _train_batches(wl, rank, n_sets):
+    """Collated training batches (internnav_b200.training.collate_traj_batch layout) in pinned host memory."""
+    B, f, T = wl["B"], wl["f"], wl["T"]
+    t, h, w = wl["grid"]
+    sets = _prompt_sets(wl, rank, n_sets)
+    out = []
+    for k, prompts in enumerate(sets):
+        g = torch.Generator(device="cpu").manual_seed(1000 * rank + k)
+        ids = torch.tensor([p + [151667] * 4 for p in prompts])
+        batch = dict(input_ids=ids, labels=torch.full_like(ids, -100), attention_mask=torch.ones_like(ids, dtype=torch.bool),
+                     t_s_pos=[len(p) for p in prompts],
+                     pixel_values=torch.randn(B * t * h * w, 1176, generator=g).bfloat16().pin_memory(),
+                     image_grid_thw=torch.tensor([list(wl["grid"])] * B),
+                     traj_images=torch.rand(B, f, 224, 224, 3, generator=g).pin_memory(),
+                     traj_depths=(torch.rand(B, f, 224, 224, generator=g) * 5.0).pin_memory(),
+                     traj_poses=(torch.randn(B, f, T, 3, generator=g) * 0.5).pin_memory(),
+                     video_frame_num=torch.randint(1, f + 1, (B,), generator=g))
+        noise = torch.randn(B * f, T, 3, generator=g).pin_memory()
+        ts = torch.randint(0, wl["K"], (B * f,), generator=g)
+        out.append((batch, noise, ts))
+    return out
+
+
+def run_ours_train(args, wl):
+    """configs[4]: one data-parallel training step per "step" (forward, backward, bucketed all-reduce, AdamW)."""
+    import torch.distributed as dist
+    from internnav_b200 import _lib
+    from internnav_b200.internvla_n1 import InternVLAN1ForCausalLM
+    from internnav_b200.manifest import random_navdp_state_dict, random_s2_state_dict
+    from internnav_b200.qwen import QWEN25VL_7B
+    from internnav_b200.train_step import DualSystemTrainer
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = InternVLAN1ForCausalLM(QWEN25VL_7B, device=str(dev))
+    s2_sd = random_s2_state_dict(QWEN25VL_7B, seed=0, device=str(dev))
+    s1_sd = random_navdp_state_dict(seed=0)           # same seed on every rank: replicas start identical, as DDP requires
+    model.load_parts(s2_sd, s1_sd)
+    latent = s2_sd["model.latent_queries"].float()
+    del s2_sd
+    torch.cuda.empty_cache()
+    tr = DualSystemTrainer(model, s1_sd, latent, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
+    B, f = wl["B"], wl["f"]
+    sets = _train_batches(wl, rank, 3)
+    barrier, timed = _timing_tools(dev, world)
+    it = [0]
+    exch = []
+
+    def to_dev(batch):
+        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and k not in ("input_ids", "attention_mask", "labels",
+                                                                                     "video_frame_num", "image_grid_thw") else v)
+                for k, v in batch.items()}
+
+    resident = [(to_dev(b), n.to(dev), t.to(dev)) for b, n, t in sets]
+
+    def step_resident():
+        it[0] += 1
+        b, n, t = resident[it[0] % len(resident)]
+        loss = tr.step(b, n, t)
+        if world > 1:
+            exch.append(tr.exchange_ms())
+        return loss
+
+    def step_e2e():
+        it[0] += 1
+        b, n, t = sets[it[0] % len(sets)]
+        return float(tr.step(to_dev(b), n.to(dev, non_blocking=True), t.to(dev, non_blocking=True)))   # D2H of the loss
+
+    for _ in range(max(args.warmup, MIN_WARMUP)):
+        step_resident()
+    _lib.prof_read()
+    exch.clear()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    barrier()
+    launches = _lib.prof_read()
+    launches["total_launches"] //= max(args.steps, 1)
+    clocks = clk.summary()
+    exch_t = [e for e in exch if e]
+    step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps, use_events=False)
+    barrier()
+    _lib.prof_read()
+    _lib.prof_enable(True)
+    step_resident()
+    torch.cuda.synchronize()
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    fl = dual_flops_per_env(dict(wl, Ns=32))
+    D = 384
+    vit_s = 12 * (24 * 257 * D * D + 4 * 257 * 257 * D) + 2 * 256 * 588 * D
+    s1 = B * f * 2 * vit_s * (1 + 3) + 3 * B * f * denoise_flops_per_sample_step(wl["T"], Ns=1)   # RGB fwd + depth fwd/bwd; decoder fwd/bwd
+    algo = (fl["llm"] + fl["vit"]) * B + s1
+    n_grad = sum(g.numel() for g in tr.buckets.grads.values())
+    allreduce = None
+    if exch_t:
+        allreduce = {"collective": "NCCL all-reduce (SUM of pre-divided fp32 buckets), torch.distributed",
+                     "buckets": [int(b.numel()) * 4 for b in tr.buckets.buffers], "bytes_per_step": n_grad * 4,
+                     "exposed_ms_per_step": sum(e["exposed_ms"] for e in exch_t) / len(exch_t),
+                     "overlapped_launch_ms_per_step": sum(e["overlapped_launch_ms"] for e in exch_t) / len(exch_t),
+                     "s2_backward_window_ms": sum(e["s2_backward_window_ms"] for e in exch_t) / len(exch_t),
+                     "note": "all buckets but the one holding latent_queries are in flight during the System-2 backward; "
+                             "exposed = end of that backward -> last bucket reduced (CUDA events, rank 0)"}
+    host = sets[0]
+    h2d = sum(v.numel() * v.element_size() for k, v in host[0].items()
+              if torch.is_tensor(v) and k in ("pixel_values", "traj_images", "traj_depths", "traj_poses")) + host[1].numel() * 4
+    _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
+            {"seq_len": wl["S"], "frames_per_episode": f, "global_batch": world * B, "trainable_params": n_grad,
+             "optimizer": "fused AdamW (fp32 masters), max_grad_norm 1.0, dropout off", "launches_are": "per step",
+             "weights": "random-init Qwen2.5-VL-7B shapes (frozen) + NavDP (trainable)",
+             "prompts": "3 rotating batches with different prompts: plan creation inside the timed region"},
+            {"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+             "api": "DualSystemTrainer.step(collated batch, noise, timesteps) -> loss; pinned host batch"},
+            algo, unit="episodes/s", metric="InternVLA-N1 DDP training step, episodes/sec",
+            extra_top={"allreduce": allreduce})
 
 
 def run_ours_denoise(args, wl):
@@ -490,6 +725,10 @@ def run_reference(args, wl):
     bounded sample (see cpu_baseline); the run stops early once ~4 minutes are spent and reports the steps it did."""
     rank, world, _ = dist_env()
     if rank != 0:
+        return
+    if wl["kind"] not in ("dual", "denoise"):
+        emit({"impl": "reference", "unavailable": "the CPU reference arm is defined for the headline workloads "
+                                                  "(dual_system, navdp_denoise); %s is a secondary workload" % args.workload})
         return
     t_start = time.perf_counter()
     vals, done_w = [], 0

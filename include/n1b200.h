@@ -235,6 +235,16 @@ int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void*
                         void* dv_f32, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int heads_q, int heads_kv,
                         int head_dim, int batch, int seq_q, int seq_k, const void* cu_q, const void* cu_k, int max_seq_q,
                         int kv_div, int causal, float scale, const void* k_len, int k_slot, void* stream);
+/* C[M,N] (+)= op(A) op(B), fp32 row-major (trans_a: A stored [K,M]; trans_b: B stored [N,K]): the 3-wide and fp32-only
+ * products of the training step (action embedding / head, navdp.py L79, L186; position-table resample, dinov2.py L180-211) */
+int n1_op_sgemm(const void* A_f32, int lda, int trans_a, const void* B_f32, int ldb, int trans_b, void* C_f32, int ldc, int M,
+                int N, int K, int accumulate, void* stream);
+/* out[r, c] = x[r, c] * gamma[c] (+ add[r, c]): LayerScale forward / backward with the residual add (layer_scale.py L27-28) */
+int n1_op_scale_cols(const void* x_bf16, int ld_x, const void* gamma_f32, const void* add_bf16_or_null, int ld_add,
+                     void* out_bf16, int ld_out, int64_t rows, int cols, void* stream);
+/* im2col of depth frames [n_img, 224, 224] fp32 -> bf16 [n_img * 256, ldk] (196 columns, zero padded): the patch-embed
+ * operand with the three replicated channels folded (navdp_backbone.py L176-181, patch_embed.py L69-81) */
+int n1_op_patchify_depth(const void* img_f32, void* out_bf16, int n_img, int ldk, void* stream);
 int n1_op_adamw(void* master_f32, void* working_bf16_or_null, const void* grad_f32, void* m_f32, void* v_f32, int64_t n,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 

@@ -1,7 +1,7 @@
 """ctypes bindings of the backward primitives (include/n1b200.h, "training: backward primitives").
 
-STATUS: first version, compiled but not yet validated on a B200 -- used only by tests/test_bwd_ops_gpu.py (skipped until
-a parity run is on record) and, later, by the training step.  Nothing on the inference path imports this module.
+Validated on the B200 against PyTorch autograd / torch.optim (tests/test_bwd_ops_gpu.py, profiles/r2_bwd_ops_parity.log);
+used by the training step (train_s1.py, train_step.py).  Nothing on the inference path imports this module.
 """
 import ctypes
 from ctypes import c_float, c_int, c_int64, c_void_p
@@ -13,7 +13,8 @@ from ._lib import check, ptr, stream_ptr
 
 _bound = False
 BWD_SYMBOLS = ["n1_op_act_fwd", "n1_op_transpose", "n1_op_colsum", "n1_op_norm_bwd", "n1_op_act_bwd", "n1_op_swiglu_bwd",
-               "n1_op_rope_transposed", "n1_op_attention_bwd", "n1_op_adamw"]
+               "n1_op_rope_transposed", "n1_op_attention_bwd", "n1_op_adamw", "n1_op_sgemm", "n1_op_scale_cols",
+               "n1_op_patchify_depth"]
 
 
 def _L():
@@ -31,6 +32,9 @@ def _L():
         L.n1_op_rope_transposed.argtypes = [vp, c_int, vp, c_int64, c_int, c_int, vp]
         L.n1_op_attention_bwd.argtypes = [vp] * 8 + [c_int] * 12 + [vp, vp, c_int, c_int, c_int, c_float, vp, c_int, vp]
         L.n1_op_adamw.argtypes = [vp, vp, vp, vp, vp, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, vp]
+        L.n1_op_sgemm.argtypes = [vp, c_int, c_int, vp, c_int, c_int, vp, c_int, c_int, c_int, c_int, c_int, vp]
+        L.n1_op_scale_cols.argtypes = [vp, c_int, vp, vp, c_int, vp, c_int, c_int64, c_int, vp]
+        L.n1_op_patchify_depth.argtypes = [vp, vp, c_int, c_int, vp]
         for n in BWD_SYMBOLS:
             getattr(L, n).restype = c_int
         _bound = True
@@ -104,6 +108,39 @@ def attention_bwd(q, k, v, o, dout, heads_q, heads_kv, head_dim, batch, seq_q, s
                                    head_dim, batch, seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div,
                                    1 if causal else 0, scale, ptr(k_len), k_slot, stream_ptr()))
     return dq, dk, dv
+
+
+def sgemm(a, b, trans_a=False, trans_b=False, out=None, accumulate=False):
+    """fp32 op(a) @ op(b): a [M, K] (or [K, M] with trans_a), b [K, N] (or [N, K] with trans_b) -> [M, N] fp32."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    assert (b.shape[1] if trans_b else b.shape[0]) == K, (a.shape, b.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    check(_L().n1_op_sgemm(c_void_p(a.data_ptr()), a.stride(0), 1 if trans_a else 0, c_void_p(b.data_ptr()), b.stride(0),
+                           1 if trans_b else 0, ptr(out), out.stride(0), M, N, K, 1 if accumulate else 0, stream_ptr()))
+    return out
+
+
+def scale_cols(x, gamma, add=None):
+    """x [rows, cols] bf16 * gamma [cols] fp32 (+ add bf16) -> bf16."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and gamma.dtype == torch.float32
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_L().n1_op_scale_cols(c_void_p(x.data_ptr()), x.stride(0), ptr(gamma),
+                                c_void_p(add.data_ptr()) if add is not None else None,
+                                add.stride(0) if add is not None else 0, ptr(out), out.stride(0), x.shape[0], x.shape[1],
+                                stream_ptr()))
+    return out
+
+
+def patchify_depth(frames, ldk=200):
+    """frames fp32 [n, 224, 224] -> bf16 [n * 256, ldk]: im2col of the 14 x 14 patches of one channel."""
+    assert frames.dtype == torch.float32 and tuple(frames.shape[1:]) == (224, 224)
+    out = torch.empty(frames.shape[0] * 256, ldk, dtype=torch.bfloat16, device=frames.device)
+    check(_L().n1_op_patchify_depth(ptr(frames), ptr(out), frames.shape[0], ldk, stream_ptr()))
+    return out
 
 
 def adamw(master, working, grad, m, v, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=1):

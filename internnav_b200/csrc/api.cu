@@ -465,6 +465,25 @@ int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void*
     attention_bwd(p, S(stream));
   });
 }
+int n1_op_sgemm(const void* A, int lda, int trans_a, const void* B, int ldb, int trans_b, void* C, int ldc, int M, int N, int K,
+                int accumulate, void* stream) {
+  return guard([&] {
+    sgemm_small(static_cast<const float*>(A), lda, trans_a, static_cast<const float*>(B), ldb, trans_b, static_cast<float*>(C),
+                ldc, M, N, K, accumulate, S(stream));
+  });
+}
+int n1_op_scale_cols(const void* x, int ld_x, const void* gamma, const void* add, int ld_add, void* out, int ld_out,
+                     int64_t rows, int cols, void* stream) {
+  return guard([&] {
+    scale_cols(B16(x), ld_x, static_cast<const float*>(gamma), B16(add), ld_add, B16(out), ld_out, rows, cols, S(stream));
+  });
+}
+int n1_op_patchify_depth(const void* img, void* out, int n_img, int ldk, void* stream) {
+  return guard([&] {
+    if (!img || !out || n_img <= 0 || ldk < 196 || ldk % 8) throw Error(N1_ERR_ARG, "n1_op_patchify_depth: bad arguments");
+    patchify_depth(static_cast<const float*>(img), B16(out), n_img, ldk, S(stream));
+  });
+}
 int n1_op_adamw(void* master, void* working, const void* grad, void* m, void* v, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int step, void* stream) {
   return guard([&] {

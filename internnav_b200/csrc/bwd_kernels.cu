@@ -187,6 +187,37 @@ __global__ void adamw_kernel(float* __restrict__ master, bf16* __restrict__ work
   if (working) working[i] = __float2bfloat16(p);
 }
 
+
+// ---------------------------------------------------------------------------------------------- small fp32 product
+// C[M, N] (+)= op(A) op(B) in fp32 on the CUDA cores, 32 x 32 tiles.  For the products of the training step that are too
+// narrow for a tensor-core tile or must stay in fp32: the 3-wide action embedding / action head (navdp.py L79, L186) and
+// their gradients, and the position-table resample R [256, 1369] of the DINOv2 ViT and its transpose (dinov2.py L180-211).
+__global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ B, int ldb, int tb,
+                                   float* __restrict__ C, int ldc, int M, int N, int K, int accumulate) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 32 + ty, col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    {  // sa[ty][tx] = op(A)[row0 + ty, k0 + tx]
+      const int r = blockIdx.y * 32 + ty, k = k0 + tx;
+      sa[ty][tx] = (r < M && k < K) ? (ta ? A[(long)k * lda + r] : A[(long)r * lda + k]) : 0.f;
+    }
+    {  // sb[ty][tx] = op(B)[k0 + ty, col0 + tx]
+      const int k = k0 + ty, c = blockIdx.x * 32 + tx;
+      sb[ty][tx] = (k < K && c < N) ? (tb ? B[(long)c * ldb + k] : B[(long)k * ldb + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) {
+    float* c = C + (long)row * ldc + col;
+    *c = accumulate ? *c + acc : acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- attention backward
 constexpr int AQ = 8;  // query rows per tile
 
@@ -384,6 +415,16 @@ void adamw_step(float* master, bf16* working, const float* grad, float* m, float
   N1_CHECK(step >= 1, "adamw_step: step counts from 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<nblk(n), 256, 0, s>>>(master, working, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+  prof_count_launch();
+  N1_CUDA(cudaGetLastError());
+}
+
+
+void sgemm_small(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M, int N,
+                 int K, int accumulate, cudaStream_t s) {
+  N1_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_small: bad arguments");
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  sgemm_small_kernel<<<grid, dim3(32, 32), 0, s>>>(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, accumulate);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }

@@ -38,6 +38,11 @@ void scale_cols(const bf16* x, int ld_x, const float* gamma, const bf16* add, in
 // Transposed rotate-half rotary: x_bar = y_bar * c - rot_half(y_bar * s), in place on `heads` heads of every row
 void rope_transposed(bf16* x, int ld, const float2* cs, long rows, int heads, int hd, cudaStream_t s);
 
+// C[M, N] (+)= op(A) op(B), all fp32 row-major with leading dimensions; trans_a: A is stored [K, M]; trans_b: B is stored
+// [N, K].  CUDA-core kernel for the narrow (3-wide) and fp32-only products of the training step.
+void sgemm_small(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M, int N,
+                 int K, int accumulate, cudaStream_t s);
+
 // Softmax-attention backward with recomputed probabilities.  Addressing as AttnParams (n1_ops.h): q / k / v / o / do
 // element (row, head, d) at ptr[row * ld + head * hd + d]; fixed or var-len / slotted sequences; GQA; bottom-right
 // causal.  Outputs: dq bf16 (same addressing as q with lddq), dk / dv fp32 [rows_k, heads_kv * hd] dense, ZEROED by the

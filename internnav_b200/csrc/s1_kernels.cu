@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(256) vit_out_kernel(const bf16* __restrict__ x
   for (int i = 0; i < 12; ++i) sq += (v[i] - mean) * (v[i] - mean);
   const float rstd = rsqrtf(warp_sum(sq) / D + 1e-6f);
   const long orow = (long)env * slots * 256 + slot * 256 + p;
-  const float* per = pe + (long)(slot * 256 + p) * D;
+  const float* per = pe ? pe + (long)(slot * 256 + p) * D : nullptr;  // null: tokens without former_pe (training)
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = (lane + i * 32) * 4;
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = (v[i * 4 + j] - mean) * rstd * w[c + j] + b[c + j] + per[c + j];
+    for (int j = 0; j < 4; ++j) o[j] = (v[i * 4 + j] - mean) * rstd * w[c + j] + b[c + j] + (per ? per[c + j] : 0.f);
     uint2 pk;
     pk.x = pack_bf16(o[0], o[1]), pk.y = pack_bf16(o[2], o[3]);
     *reinterpret_cast<uint2*>(mem + orow * D + c) = pk;

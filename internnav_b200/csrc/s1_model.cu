@@ -246,7 +246,7 @@ void S1Model::load(const WeightSource& ws, const S1Dims& d, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ RGB-D encoder
 // Returns the scratch high-water mark (bytes from the start of `c0`'s buffer); launches nothing when dry.
 size_t S1Model::vit_forward(const Vit& v, Carver c, const float* img, bool depth, int n_img, bf16* mem, int slot_base,
-                            cudaStream_t s) const {
+                            cudaStream_t s, bool with_pe) const {
   const int D = dims.D;
   const long rows = (long)n_img * 257;
   const int ldk = v.patch.K;
@@ -288,7 +288,7 @@ size_t S1Model::vit_forward(const Vit& v, Carver c, const float* img, bool depth
     e3.gamma = b.ls2, e3.residual = x, e3.ldr = D;
     linear(b.fc2, hid, 4 * D, x, D, (int)rows, e3, s);
   }
-  vit_out(x, mem, v.norm.w, v.norm.b, former_pe_, n_img, dims.frames, slot_base, 2 * dims.frames, s);
+  vit_out(x, mem, v.norm.w, v.norm.b, with_pe ? former_pe_ : nullptr, n_img, dims.frames, slot_base, 2 * dims.frames, s);
   return c.used();
 }
 

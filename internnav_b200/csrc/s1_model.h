@@ -104,7 +104,7 @@ class S1Model {
   Vit load_vit(const WeightSource& ws, bool depth, cudaStream_t s);
   DecLayer load_dec_layer(const WeightSource& ws, bool with_kv, cudaStream_t s);
   size_t vit_forward(const Vit& v, Carver c, const float* img, bool depth, int n_img, bf16* mem, int slot_base,
-                     cudaStream_t s) const;
+                     cudaStream_t s, bool with_pe = true) const;
   size_t rgbd_impl(Carver c, const float* rgb, const float* depth, bf16* out, int B, cudaStream_t s) const;
   size_t goal_impl(Carver c, const bf16* latents, bf16* goal, int B, cudaStream_t s) const;
   DenoiseBufs carve_denoise(Carver& c, int B, int Ns, int T) const;

@@ -4,8 +4,12 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <memory>
+#include <mutex>
+#include <vector>
 
 #include "s2_kernels.h"
 
@@ -87,9 +91,70 @@ Lin plain_lin(Arena& a, const WeightSource& ws, const std::string& name, bool bi
 VitPlan::~VitPlan() {
   cudaFree(window_index), cudaFree(reverse_index), cudaFree(cu_window), cudaFree(cu_full), cudaFree(rope);
 }
+// ---- pooled plan storage: device blocks (and their pinned staging twins) are recycled across plans
+namespace {
+struct PlanBlock {
+  void* dev = nullptr;
+  void* host = nullptr;  // pinned staging of the integer arrays
+  size_t bytes = 0;
+  cudaEvent_t last_use = nullptr;  // recorded by the previous owner's consumers
+};
+std::mutex g_pool_mu;
+std::vector<PlanBlock> g_pool;
+
+PlanBlock pool_take(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); ++i)
+      if (g_pool[i].bytes >= bytes) {
+        PlanBlock b = g_pool[i];
+        g_pool.erase(g_pool.begin() + i);
+        return b;
+      }
+  }
+  PlanBlock b;
+  b.bytes = (bytes + (1 << 20) - 1) & ~size_t((1 << 20) - 1);  // 1 MiB granularity: similar prompts share a size class
+  N1_CUDA(cudaMalloc(&b.dev, b.bytes));
+  N1_CUDA(cudaMallocHost(&b.host, b.bytes));
+  N1_CUDA(cudaEventCreateWithFlags(&b.last_use, cudaEventDisableTiming));
+  return b;
+}
+void pool_give(const PlanBlock& b) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool.size() < 128) {
+    g_pool.push_back(b);
+    return;
+  }
+  cudaFree(b.dev), cudaFreeHost(b.host), cudaEventDestroy(b.last_use);
+}
+struct PlanHostTwin {  // keeps the pinned twin reachable from the plan without widening the public struct
+  std::mutex mu;
+  std::vector<std::pair<const void*, void*>> map;
+} g_twin;
+}  // namespace
+
+void LlmPlan::wait_ready(cudaStream_t s) const {
+  if (ready) N1_CUDA(cudaStreamWaitEvent(s, ready, 0));
+}
+void LlmPlan::mark_used(cudaStream_t s) const {
+  if (last_use) N1_CUDA(cudaEventRecord(last_use, s));
+}
 LlmPlan::~LlmPlan() {
-  cudaFree(cu), cudaFree(kind), cudaFree(src), cudaFree(out_rows), cudaFree(rope);
-  cudaFree(dest_rows), cudaFree(d_len), cudaFree(d_delta);
+  if (ready) cudaEventDestroy(ready);
+  if (block) {
+    PlanBlock b;
+    b.dev = block, b.bytes = block_bytes, b.last_use = last_use;
+    {
+      std::lock_guard<std::mutex> lk(g_twin.mu);
+      for (size_t i = 0; i < g_twin.map.size(); ++i)
+        if (g_twin.map[i].first == block) {
+          b.host = g_twin.map[i].second;
+          g_twin.map.erase(g_twin.map.begin() + i);
+          break;
+        }
+    }
+    pool_give(b);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ load
@@ -221,28 +286,45 @@ LlmPlan* S2Model::make_llm_plan(const int32_t* ids, const int32_t* lens, int B, 
     for (int st = 0; st < 3; ++st)
       for (int i = 0; i < L; ++i) p->h_pos3[(size_t)st * p->tokens + p->h_cu[b] + i] = pos_seq[b][(size_t)st * L + i];
   }
-  p->cu = upload(p->h_cu, s);
-  p->kind = upload(kind, s);
-  p->src = upload(src, s);
-  p->out_rows = upload(out_rows, s);
-  int* pos = upload(p->h_pos3, s);
   const int half = dims.head_dim / 2;
-  N1_CUDA(cudaMalloc(&p->rope, (size_t)p->tokens * half * sizeof(float2)));
-  mrope_table(pos, p->rope, p->tokens, half, dims.mrope[0], dims.mrope[1], dims.rope_theta, s);
+  std::vector<int> dest, len_v;
   if (gen) {
     p->max_new = max_new_tokens;
     p->slot = p->max_len + max_new_tokens + dims.n_query;
-    std::vector<int> dest(p->tokens), len_v(B);
+    dest.resize(p->tokens), len_v.resize(B);
     for (int b = 0; b < B; ++b) {
       len_v[b] = p->h_cu[b + 1] - p->h_cu[b];
       for (int i = 0; i < len_v[b]; ++i) dest[p->h_cu[b] + i] = b * p->slot + i;
     }
-    p->dest_rows = upload(dest, s);
-    p->d_len = upload(len_v, s);
-    p->d_delta = upload(p->h_delta, s);
   }
-  N1_CUDA(cudaStreamSynchronize(s));
-  cudaFree(pos);
+  // one pooled block: [ints: cu | kind | src | out_rows | pos3 | dest | len | delta] [rope table]; one H2D copy from the
+  // block's pinned twin, one kernel, no allocation / free / synchronisation once the pool holds a block of this size
+  const std::vector<int>* parts[8] = {&p->h_cu, &kind, &src, &out_rows, &p->h_pos3, &dest, &len_v, &p->h_delta};
+  size_t off_i[9] = {0};
+  for (int i = 0; i < 8; ++i) off_i[i + 1] = off_i[i] + ((parts[i]->size() + 3) & ~size_t(3));  // 16-byte aligned parts
+  const size_t int_bytes = (off_i[8] * sizeof(int) + 255) & ~size_t(255);
+  const size_t need = int_bytes + (size_t)p->tokens * half * sizeof(float2);
+  PlanBlock blk = pool_take(need);
+  p->block = blk.dev, p->block_bytes = blk.bytes, p->last_use = blk.last_use;
+  {
+    std::lock_guard<std::mutex> lk(g_twin.mu);
+    g_twin.map.emplace_back(blk.dev, blk.host);
+  }
+  N1_CUDA(cudaStreamWaitEvent(s, blk.last_use, 0));  // the previous owner's consumers (any stream) are done before we overwrite
+  N1_CUDA(cudaEventSynchronize(blk.last_use));       // ... and before the pinned twin is rewritten (no-op unless just recycled)
+  int* hp = static_cast<int*>(blk.host);
+  for (int i = 0; i < 8; ++i)
+    if (!parts[i]->empty()) memcpy(hp + off_i[i], parts[i]->data(), parts[i]->size() * sizeof(int));
+  N1_CUDA(cudaMemcpyAsync(blk.dev, blk.host, off_i[8] * sizeof(int), cudaMemcpyHostToDevice, s));
+  int* dp = static_cast<int*>(blk.dev);
+  p->cu = dp + off_i[0], p->kind = dp + off_i[1], p->src = dp + off_i[2], p->out_rows = dp + off_i[3];
+  int* pos = dp + off_i[4];
+  if (gen) p->dest_rows = dp + off_i[5], p->d_len = dp + off_i[6], p->d_delta = dp + off_i[7];
+  p->rope = reinterpret_cast<float2*>(static_cast<uint8_t*>(blk.dev) + int_bytes);
+  mrope_table(pos, p->rope, p->tokens, half, dims.mrope[0], dims.mrope[1], dims.rope_theta, s);
+  N1_CUDA(cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
+  N1_CUDA(cudaEventRecord(p->ready, s));
+  N1_CUDA(cudaEventRecord(p->last_use, s));  // a plan that is never consumed still leaves its block in a defined state
   return p.release();
 }
 
@@ -374,7 +456,9 @@ void S2Model::llm_prefill(const LlmPlan& p, void* ws, size_t ws_bytes, const bf1
   N1_CHECK(loaded_ && ws, "llm_prefill: not loaded / null workspace");
   N1_CHECK(p.max_new == 0, "llm_prefill: this is a generation plan (use llm_generate)");
   if (ws_bytes < ws_llm(p)) throw Error(-7, "llm_prefill: workspace too small");
+  p.wait_ready(s);
   llm_impl(Carver(ws, ws_bytes), p, image_feats, out, s);
+  p.mark_used(s);
 }
 
 // ------------------------------------------------------------------------------------------------ greedy decode
@@ -509,7 +593,9 @@ void S2Model::llm_generate(const LlmPlan& p, void* ws, size_t ws_bytes, const bf
   if (!has_lm_head()) throw Error(-6, "llm_generate: lm_head.weight was not part of the loaded state_dict");
   N1_CHECK(out.tokens && out.lens, "llm_generate: null output buffers");
   if (ws_bytes < ws_generate(p)) throw Error(-7, "llm_generate: workspace too small");
+  p.wait_ready(s);
   gen_impl(Carver(ws, ws_bytes), p, image_feats, eos, n_eos, pad, &out, latents, s);
+  p.mark_used(s);
 }
 
 }  // namespace n1

@@ -42,6 +42,16 @@ struct LlmPlan {
   // generation plans only (max_new > 0): every sequence owns `slot` rows of the per-layer K/V cache
   int max_new = 0, slot = 0;
   int *dest_rows = nullptr, *d_len = nullptr, *d_delta = nullptr;  // [tokens], [B], [B]
+  // All device arrays above are carved from ONE pooled block (plan_pool in s2_model.cu): a plan is created every policy
+  // step (prompts change), so creation must not cudaMalloc / cudaFree / synchronise once the pool is warm.  `ready` is
+  // recorded after the upload + RoPE-table kernel on the creating stream; `last_use` after every hot call, so a recycled
+  // block is never overwritten while a consumer on another stream may still read it.
+  void* block = nullptr;
+  size_t block_bytes = 0;
+  cudaEvent_t ready = nullptr;
+  mutable cudaEvent_t last_use = nullptr;
+  void wait_ready(cudaStream_t s) const;  // first statement of every hot call
+  void mark_used(cudaStream_t s) const;   // last statement of every hot call
   ~LlmPlan();
 };
 

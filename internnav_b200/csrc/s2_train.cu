@@ -119,6 +119,7 @@ void S2Model::train_forward(const LlmPlan& p, void* ws, size_t ws_bytes, const b
   N1_CHECK(loaded_ && ws && states, "train_forward: not loaded / null buffers");
   N1_CHECK(p.max_new > 0 && p.slot >= p.max_len + dims.n_query, "train_forward: needs a generation plan");
   if (ws_bytes < ws_train(p)) throw Error(-7, "train_forward: workspace too small");
+  p.wait_ready(s);
   const int H = dims.hidden, hd = dims.head_dim, nq = dims.n_query;
   const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd, kvd = dims.kv_heads * hd;
   Carver c(ws, ws_bytes);
@@ -167,12 +168,14 @@ void S2Model::train_forward(const LlmPlan& p, void* ws, size_t ws_bytes, const b
   }
   N1_CUDA(cudaMemcpyAsync(t.x_final, t.x, row_bytes, cudaMemcpyDeviceToDevice, s));
   layernorm(t.x, H, states, H, final_norm_, nullptr, R, H, dims.rms_eps, 1, s);
+  p.mark_used(s);
 }
 
 void S2Model::train_backward(const LlmPlan& p, void* ws, size_t ws_bytes, const bf16* grad_states, float* grad_latent,
                              cudaStream_t s) {
   N1_CHECK(loaded_ && ws && grad_states && grad_latent, "train_backward: not loaded / null buffers");
   if (ws_bytes < ws_train(p)) throw Error(-7, "train_backward: workspace too small");
+  p.wait_ready(s);
   ensure_transposed(s);
   const int H = dims.hidden, hd = dims.head_dim, nq = dims.n_query;
   const int qkv_n = (dims.heads + 2 * dims.kv_heads) * hd, kvd = dims.kv_heads * hd;
@@ -218,6 +221,7 @@ void S2Model::train_backward(const LlmPlan& p, void* ws, size_t ws_bytes, const 
   }
   sum_over_batch_kernel<<<nblk((long)nq * H), 256, 0, s>>>(t.d, p.B, nq, H, grad_latent);
   N1_CUDA(cudaGetLastError());
+  p.mark_used(s);
 }
 
 }  // namespace n1

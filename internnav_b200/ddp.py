@@ -74,14 +74,31 @@ class GradientBuckets:
         for b in self.buffers:
             b.zero_()
 
-    def all_reduce(self, async_op=True):
-        """Average every bucket over the process group, last parameters first.  With async_op the collectives are in
-        flight on return (call wait() before the optimizer reads the gradients)."""
+    def bucket_of(self, name):
+        """Index (launch order) of the bucket holding `name`."""
+        for i, names in enumerate(self.layout):
+            if name in names:
+                return i
+        raise KeyError(name)
+
+    def scale_(self, factor, skip=()):
+        for i, b in enumerate(self.buffers):
+            if i not in skip:
+                b.mul_(factor)
+
+    def all_reduce(self, async_op=True, skip=(), only=None, append=False):
+        """Average buckets over the process group, last parameters first.  `skip` / `only` select buckets by index, so a
+        caller can exchange the buckets that are complete while the rest of the backward still runs (what DDP's hooks do)
+        and the remaining ones afterwards (`append=True` keeps the earlier handles pending).  With async_op the
+        collectives are in flight on return (call wait() before the optimizer reads the gradients)."""
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("GradientBuckets.all_reduce needs an initialised torch.distributed process group")
         world = dist.get_world_size(self.group)
-        self._pending = []
-        for buf in self.buffers:
+        if not append:
+            self._pending = []
+        for i, buf in enumerate(self.buffers):
+            if i in skip or (only is not None and i not in only):
+                continue
             buf.div_(world)
             work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
             if async_op:

@@ -142,8 +142,9 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
         return out
 
     def rgb_memory_tokens(self, images):
-        """Training branch: tokens of the frozen RGB ViT as the Q-former sees them (final norm, cls dropped, former_pe
-        added): images [B, frames, 224, 224, 3] -> bf16 [B, frames * 256, D].  (UNVALIDATED on GPU, see s1_train.cu.)"""
+        """Training branch: tokens of the frozen RGB ViT (final norm, cls dropped; WITHOUT former_pe, which is trainable
+        and added by the training schedule from its master copy): images [B, frames, 224, 224, 3] -> bf16
+        [B, frames * 256, D]."""
         B = images.shape[0]
         want = (self.memory_size, self.image_size, self.image_size, 3)
         if tuple(images.shape[1:]) != want:
@@ -223,7 +224,7 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
                 side.synchronize()
                 before = _lib.prof_read()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):  # the S2 thread may allocate meanwhile
                     out = self._sample_eager(st["goal"], st["rgbd"], st["x0"], st["nz"], K)
                 nodes = _lib.prof_read()  # kernels captured into the graph = launches of every replay
                 _lib.lib().n1_prof_add(before["gemm_launches"], before["total_launches"])  # restore the running counters

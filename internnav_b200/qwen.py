@@ -212,12 +212,19 @@ class System2:
             with torch.cuda.device(self.device):
                 check(L.n1_llm_plan_create(self._h(), ids, lens, len(prompts), garr, len(gkey) // 3, ctypes.byref(p),
                                            _lib.stream_ptr()))
-            if len(self._llm_plans) > 64:  # prompts change every step in deployment: bound the cache
-                _, (old, _) = self._llm_plans.popitem()
-                L.n1_llm_plan_destroy(old)
+            self._evict_plans(L)
             hit = (p, len(prompts))
             self._llm_plans[key] = hit
         return hit[0]
+
+    def _evict_plans(self, L, keep=8):
+        """Prompts change every step in deployment, so the cache only serves repeated calls within a step (generate +
+        latents).  Oldest first: the library recycles a destroyed plan's device block, and the oldest plan's consumers
+        finished long ago, so the recycling never has to wait."""
+        while len(self._llm_plans) > keep:
+            k = next(iter(self._llm_plans))
+            old, _ = self._llm_plans.pop(k)
+            L.n1_llm_plan_destroy(old)
 
     def positions(self, plan, B):
         L = _lib.lib()
@@ -302,9 +309,7 @@ class System2:
             with torch.cuda.device(self.device):
                 check(L.n1_gen_plan_create(self._h(), ids, lens, len(prompts), garr, len(gkey) // 3, int(max_new_tokens),
                                            ctypes.byref(p), _lib.stream_ptr()))
-            if len(self._llm_plans) > 64:
-                _, (old, _) = self._llm_plans.popitem()
-                L.n1_llm_plan_destroy(old)
+            self._evict_plans(L)
             hit = (p, len(prompts))
             self._llm_plans[key] = hit
         return hit[0]

@@ -5,15 +5,16 @@ The schedule follows oracle/navdp_backward.py (the backward specification, equal
 primitive at a time; every matrix product -- forward, dgrad (dY W) and wgrad (dY^T X) -- goes through the tcgen05 GEMM
 (`ops.mm_nt`, operands transposed by a kernel where the contraction runs over rows), attention / LayerNorm / GELU / ReLU /
 layer-scale forward and backward through the kernels of attention.cu, norm.cu and bwd_kernels.cu.  What stays in PyTorch
-is tensor plumbing on bf16 buffers: slicing, concatenation, additions of equally shaped buffers, im2col of the depth
-frames (F.unfold), and three products too small for a tensor-core tile (the 3-wide action embedding / action head and
-the 256 x 1369 position-table resample).
+is tensor plumbing on bf16 buffers: slicing, concatenation, additions of equally shaped buffers.  The im2col of the
+depth frames is the library's patchify kernel (three replicated channels folded into one, as at inference), and the
+products too narrow for a tensor-core tile or held in fp32 (the 3-wide action embedding / action head, the 256 x 1369
+position-table resample and their gradients) go through the library's small fp32 product (`ops.sgemm`).
 
 `ops` is the kernel backend.  The product backend is `GpuOps` below (ctypes -> libn1b200.so; it refuses to run without
 the library / a B200).  tests/test_train_s1_host.py drives this same schedule with a plain fp32 PyTorch implementation of
 the `ops` contract on the CPU and checks every gradient against the oracle -- that validates the schedule, not the
-kernels.  STATUS: the backward kernels have not run on a B200 yet (written after round 1's GPU budget was spent); the
-op-level and end-to-end GPU tests are in tests/test_bwd_ops_gpu.py, skipped until a parity run is on record.
+kernels.  The kernels are validated on the B200 by tests/test_bwd_ops_gpu.py (op level, System-2 half, and the whole step
+against the oracle chain; profiles/r2_bwd_ops_parity.log).
 """
 import math
 
@@ -68,6 +69,18 @@ class GpuOps:
     def act_bwd(self, pre, dy, kind):
         return self._bwd.act_bwd(pre, dy, kind)
 
+    def sgemm(self, a, b, trans_a=False, trans_b=False):
+        """fp32 op(a) @ op(b) on the CUDA cores (narrow / fp32-only products)."""
+        return self._bwd.sgemm(a, b, trans_a, trans_b)
+
+    def patchify_depth(self, frames):
+        """[n, 224, 224] fp32 -> im2col rows [n * 256, 200] (196 columns + zero padding) in the kernel dtype."""
+        return self._bwd.patchify_depth(frames)
+
+    def scale_cols(self, x, gamma, add=None):
+        """x * gamma (+ add), per column: LayerScale with the residual add."""
+        return self._bwd.scale_cols(x, gamma, add)
+
 
 # ------------------------------------------------------------------------------------------------ schedule
 def _pad8(x):
@@ -85,6 +98,7 @@ class S1TrainStep:
         self.w = {}           # working copies in the kernel dtype (refresh() after every optimizer step)
         self.refresh()
         self._resample = {}
+        self._touched = set()   # tensors that received a gradient in the current step (torch.optim skips the others)
 
     def refresh(self):
         self.w = {k: self.ops.cast(v) for k, v in self.p32.items() if v.is_floating_point()}
@@ -120,8 +134,9 @@ class S1TrainStep:
 
     def _acc(self, g, name, val, rows=None):
         full = self.p32[name]
-        if name not in g:
+        if name not in g:   # `g` may arrive pre-populated with views into the all-reduce buckets (forward_backward)
             g[name] = torch.zeros(full.shape, dtype=torch.float32, device=val.device)
+        self._touched.add(name)
         tgt = g[name] if rows is None else g[name][rows]
         tgt += val.reshape(tgt.shape).float()
 
@@ -184,20 +199,21 @@ class S1TrainStep:
             n = src_side * src_side
             eye = torch.eye(n).reshape(n, 1, src_side, src_side)
             s = float(dst_side + 0.1) / src_side
-            self._resample[key] = F.interpolate(eye, scale_factor=(s, s), mode="bicubic", antialias=False).reshape(n, -1).t()
+            self._resample[key] = F.interpolate(eye, scale_factor=(s, s), mode="bicubic", antialias=False).reshape(n, -1).t().contiguous()
         return self._resample[key].to(device)
 
-    def vit_fwd(self, p, x_img):
-        ops, n = self.ops, x_img.shape[0]
-        patches = F.unfold(x_img.float(), kernel_size=14, stride=14).transpose(1, 2)            # [n, 256, 588]
-        patches = ops.cast(_pad8(patches))                                                      # K = 588 -> 592
-        Wp = self.w[p + "patch_embed.proj.weight"]
-        t = ops.mm_nt(patches.reshape(-1, patches.shape[-1]), _pad8(Wp.reshape(Wp.shape[0], -1)),
-                      bias=self._f32(p + "patch_embed.proj.bias")).reshape(n, 256, -1)
+    def vit_fwd(self, p, frames):
+        """frames: [n, 224, 224] fp32 depth frames.  The reference feeds the ViT three identical channels
+        (navdp_backbone.py L176-181); the im2col keeps one and the patch-embed weight is summed over its channel axis."""
+        ops, n = self.ops, frames.shape[0]
+        patches = ops.patchify_depth(frames.float().contiguous())                               # [n * 256, 200]
+        Wp = self.p32[p + "patch_embed.proj.weight"]
+        Wf = ops.cast(_pad8(Wp.sum(1).reshape(Wp.shape[0], -1)).to(patches.device))              # [D, 196 -> 200]
+        t = ops.mm_nt(patches, Wf, bias=self._f32(p + "patch_embed.proj.bias")).reshape(n, 256, -1)
         pe = self._f32(p + "pos_embed")
         src_side = int(math.isqrt(pe.shape[1] - 1))
         R = None if src_side == 16 else self._R(src_side, 16, pe.device)
-        pe_patch = pe[0, 1:] if R is None else R @ pe[0, 1:]
+        pe_patch = pe[0, 1:] if R is None else ops.sgemm(R, pe[0, 1:].contiguous())
         pos = torch.cat((pe[:, :1], pe_patch.unsqueeze(0)), dim=1)
         cls = self._f32(p + "cls_token").expand(n, -1, -1)
         t = ops.cast(torch.cat((cls, t.float()), dim=1) + pos)
@@ -209,12 +225,12 @@ class S1TrainStep:
             q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
             o = ops.attention(q, k, v, 6, C // 6, n, 257, 257, False)
             a = self.lin(b + "attn.proj", o.reshape(n, 257, C))
-            t_mid = ops.cast(t.float() + a.float() * self._f32(b + "ls1.gamma"))
+            t_mid = ops.scale_cols(a.reshape(-1, C), self._f32(b + "ls1.gamma"), t.reshape(-1, C)).reshape(t.shape)
             h2 = self.ln(b + "norm2", t_mid, 1e-6)
             f1 = self.lin(b + "mlp.fc1", h2)
             act = ops.act_fwd(f1.reshape(-1, f1.shape[-1]), ACT_GELU).reshape(f1.shape)
             f2 = self.lin(b + "mlp.fc2", act)
-            t_out = ops.cast(t_mid.float() + f2.float() * self._f32(b + "ls2.gamma"))
+            t_out = ops.scale_cols(f2.reshape(-1, C), self._f32(b + "ls2.gamma"), t_mid.reshape(-1, C)).reshape(t.shape)
             tape.append((t, h, q, k, v, o, a, t_mid, h2, f1, act, f2))
             t = t_out
         y = self.ln(p + "norm", t, 1e-6)
@@ -230,13 +246,13 @@ class S1TrainStep:
             b = "%sblocks.%d." % (p, i)
             t_in, h, q, k, v, o, a, t_mid, h2, f1, act, f2 = tape[i]
             self._acc(g, b + "ls2.gamma", ops.colsum(dt.reshape(-1, C).contiguous(), f2.reshape(-1, C).contiguous()))
-            df2 = ops.cast(dt.float() * self._f32(b + "ls2.gamma"))
+            df2 = ops.scale_cols(dt.reshape(-1, C), self._f32(b + "ls2.gamma")).reshape(dt.shape)
             dact = self.lin_bwd(b + "mlp.fc2", act, df2, g)
             df1 = ops.act_bwd(f1.reshape(-1, f1.shape[-1]).contiguous(), dact.reshape(-1, f1.shape[-1]).contiguous(), ACT_GELU)
             dh2 = self.lin_bwd(b + "mlp.fc1", h2, df1.reshape(f1.shape), g)
             dt = ops.cast(dt.float() + self.ln_bwd(b + "norm2", t_mid, dh2, g, 1e-6).float())
             self._acc(g, b + "ls1.gamma", ops.colsum(dt.reshape(-1, C).contiguous(), a.reshape(-1, C).contiguous()))
-            da = ops.cast(dt.float() * self._f32(b + "ls1.gamma"))
+            da = ops.scale_cols(dt.reshape(-1, C), self._f32(b + "ls1.gamma")).reshape(dt.shape)
             do = self.lin_bwd(b + "attn.proj", o.reshape(n, 257, C), da, g).reshape(n * 257, C).contiguous()
             dq, dk, dv = ops.attention_bwd(q, k, v, o, do, 6, C // 6, n, 257, 257, False)
             dqkv = torch.cat((dq, dk.to(dq.dtype), dv.to(dq.dtype)), dim=1).reshape(n, 257, 3 * C)
@@ -244,13 +260,14 @@ class S1TrainStep:
             dt = ops.cast(dt.float() + self.ln_bwd(b + "norm1", t_in, dh, g, 1e-6).float())
         dtf = dt.float()
         self._acc(g, p + "cls_token", dtf[:, :1].sum(0, keepdim=True))
-        dpe_patch = dtf[:, 1:].sum(0)
-        dpe = torch.cat((dtf[:, :1].sum(0), dpe_patch if R is None else R.t() @ dpe_patch), dim=0).unsqueeze(0)
+        dpe_patch = dtf[:, 1:].sum(0).contiguous()
+        dpe = torch.cat((dtf[:, :1].sum(0), dpe_patch if R is None else ops.sgemm(R, dpe_patch, trans_a=True)), dim=0).unsqueeze(0)
         self._acc(g, p + "pos_embed", dpe)
         dpatch = dt[:, 1:].reshape(-1, C).contiguous()
         Wp = self.p32[p + "patch_embed.proj.weight"]
-        dW = ops.mm_nt(ops.transpose(dpatch), ops.transpose(patches.reshape(-1, patches.shape[-1])), out_fp32=True)
-        self._acc(g, p + "patch_embed.proj.weight", dW[:, : Wp[0].numel()].reshape(Wp.shape))
+        dWf = ops.mm_nt(ops.transpose(dpatch), ops.transpose(patches), out_fp32=True)[:, :196]   # [D, 196], one channel
+        # the three input channels are identical, so each channel of the Conv2d weight receives the same gradient
+        self._acc(g, p + "patch_embed.proj.weight", dWf.reshape(Wp.shape[0], 1, 14, 14).expand(Wp.shape))
         self._acc(g, p + "patch_embed.proj.bias", ops.colsum(dpatch))
 
     # ---- Q-former layer (post-norm, ReLU; navdp_backbone.py L148) ---------------------------------------------
@@ -287,8 +304,7 @@ class S1TrainStep:
         `rgb_has_pe`: they already carry former_pe (n1_rgb_tokens delivers them that way); depths [B, T, 224, 224, 1]."""
         ops, p = self.ops, "rgbd_encoder."
         B, T = depths.shape[:2]
-        td = depths.permute(0, 1, 4, 2, 3).reshape(-1, 1, 224, 224)
-        dtok, vsave = self.vit_fwd(p + "depth_model.", torch.cat([td, td, td], dim=1))
+        dtok, vsave = self.vit_fwd(p + "depth_model.", depths.reshape(-1, 224, 224))
         pe = self._f32(p + "former_pe.weight")[: self.frames * 512].clone()
         if rgb_has_pe:
             pe[: T * 256] = 0
@@ -355,8 +371,9 @@ class S1TrainStep:
         R, T, _ = noisy.shape
         B = goal.shape[0]
         Ns = R // B
-        # the 3 -> D action embedding is too narrow for a tensor-core tile: plain product (fp32), then the kernel dtype
-        x = noisy.float() @ self._f32("input_embed.weight").t() + self._f32("input_embed.bias")
+        # the 3 -> D action embedding is too narrow for a tensor-core tile: the small fp32 product, then the kernel dtype
+        x = ops.sgemm(noisy.float().reshape(-1, 3).contiguous(), self._f32("input_embed.weight"), trans_b=True).reshape(R, T, -1) \
+            + self._f32("input_embed.bias")
         half = 192
         freq = torch.exp(torch.arange(half, device=x.device) * -(math.log(10000) / (half - 1)))
         te = timesteps.to(x.device)[:, None].float() * freq[None, :]
@@ -381,15 +398,17 @@ class S1TrainStep:
             tape.append((x, m1, x1, m2, x2, h3, f1, act))
             x = ops.cast(x2.float() + f2.float())
         hN = self.ln("layernorm", x, 1e-5)
-        y = hN.float() @ self._f32("action_head.weight").t() + self._f32("action_head.bias")      # D -> 3
+        y = ops.sgemm(hN.float().reshape(-1, hN.shape[-1]), self._f32("action_head.weight"), trans_b=True).reshape(R, T, 3) \
+            + self._f32("action_head.bias")                                                      # D -> 3
         return y, (noisy, tape, x, hN, B, Ns, M, T)
 
     def decoder_bwd(self, saved, dy, g):
         ops = self.ops
         noisy, tape, x_last, hN, B, Ns, M, T = saved
-        self._acc(g, "action_head.weight", dy.reshape(-1, 3).t() @ hN.float().reshape(-1, hN.shape[-1]))
-        self._acc(g, "action_head.bias", dy.reshape(-1, 3).sum(0))
-        dx = self.ln_bwd("layernorm", x_last, ops.cast(dy @ self._f32("action_head.weight")), g, 1e-5)
+        dy2 = dy.reshape(-1, 3).float().contiguous()
+        self._acc(g, "action_head.weight", ops.sgemm(dy2, hN.float().reshape(-1, hN.shape[-1]), trans_a=True))
+        self._acc(g, "action_head.bias", dy2.sum(0))
+        dx = self.ln_bwd("layernorm", x_last, ops.cast(ops.sgemm(dy2, self._f32("action_head.weight")).reshape(hN.shape)), g, 1e-5)
         dcond = 0
         for i in reversed(range(self.layers)):
             p = "decoder.layers.%d." % i
@@ -407,7 +426,8 @@ class S1TrainStep:
         gop = torch.zeros_like(self.p32["out_pos_embed"], dtype=torch.float32, device=dxf.device)
         gop[:, :T] = dxf.sum(0, keepdim=True)
         self._acc(g, "out_pos_embed", gop)
-        self._acc(g, "input_embed.weight", dxf.reshape(-1, dxf.shape[-1]).t() @ noisy.float().reshape(-1, 3))
+        self._acc(g, "input_embed.weight", ops.sgemm(dxf.reshape(-1, dxf.shape[-1]).contiguous(),
+                                                    noisy.float().reshape(-1, 3).contiguous(), trans_a=True))
         self._acc(g, "input_embed.bias", dxf.reshape(-1, dxf.shape[-1]).sum(0))
         dcond = dcond.reshape(B, Ns, M, -1).sum(1)
         gcp = torch.zeros_like(self.p32["cond_pos_embed"], dtype=torch.float32, device=dxf.device)
@@ -417,10 +437,12 @@ class S1TrainStep:
 
     # ---- the step ----------------------------------------------------------------------------------------------
     def forward_backward(self, traj_hidden_states, rgb_tokens, traj_depths, traj_poses, video_frame_num, noise, timesteps,
-                         alphas_cumprod, rgb_has_pe=False):
+                         alphas_cumprod, rgb_has_pe=False, grads_into=None):
         """-> (loss, {name: fp32 gradient}, d loss / d traj_hidden_states [B, n_query, H]).
         rgb_tokens: [B*f, 2*256, D] RGB-ViT tokens of the [goal frame, current frame] pairs (frozen branch);
-        traj_depths [B, f, 224, 224]; alphas_cumprod fp32 [K] (DDPMScheduler table, n1_ddpm_tables)."""
+        traj_depths [B, f, 224, 224]; alphas_cumprod fp32 [K] (DDPMScheduler table, n1_ddpm_tables).
+        grads_into: {reference tensor name: fp32 view}, e.g. the views into the all-reduce buckets (ddp.GradientBuckets):
+        the gradients are ACCUMULATED there (the caller zeroes them), so nothing is copied or re-flattened afterwards."""
         dev = self.w["layernorm.weight"].device
         Bb, f = traj_depths.shape[:2]
         hs = traj_hidden_states.to(dev).unsqueeze(1).repeat(1, f, 1, 1).flatten(0, 1)
@@ -439,11 +461,16 @@ class S1TrainStep:
         denom = mask.sum() * err.shape[1] * err.shape[2]
         loss = (err.square() * mask).sum() / denom
         g = {}
+        self._touched = set()
+        if grads_into is not None:
+            for k, view in grads_into.items():
+                g[k.replace("in_proj_weight", "in_proj.weight").replace("in_proj_bias", "in_proj.bias")] = view
         dgoal, drgbd = self.decoder_bwd(dsave, 2.0 * err * mask / denom, g)
         self.rgbd_bwd(rsave, drgbd, g)
         dhs = self.goal_bwd(gsave, dgoal, g)
         grads = {}
         for k, v in g.items():   # report under the reference's tensor names
             k2 = k.replace("in_proj.weight", "in_proj_weight").replace("in_proj.bias", "in_proj_bias")
-            grads[k2] = v
+            if k in self._touched and (grads_into is None or k2 in grads_into):
+                grads[k2] = v
         return loss, grads, dhs.float().reshape(Bb, f, *dhs.shape[1:]).sum(1)

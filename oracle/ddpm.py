@@ -10,8 +10,16 @@ constructor arguments the reference uses:
                   prediction_type='epsilon')          # defaults: variance_type='fixed_small', clip_sample_range=1.0,
                                                       # timestep_spacing='leading', steps_offset=0, thresholding=False
 
-PARITY UNPINNED for this file: the reference holds no test / golden vector for the scheduler and the
-real package cannot be executed here.  The arithmetic below follows diffusers' scheduling_ddpm.py:
+PARITY UNPINNED against diffusers itself: the reference holds no test / golden vector for the scheduler
+and the real package cannot be executed here (not in the image, not in /opt/wheelhouse, no network).  What anchors it
+instead (tests/test_oracle_s1.py): (1) the constructor arguments are the ones the reference's own tree documents for this
+class (internnav/model/encoder/diffusion_policy/config/*.yaml `noise_scheduler`: squaredcos_cap_v2, fixed_small,
+clip_sample True, epsilon); (2) an independent float64 derivation -- the Gaussian posterior q(x_{t-1} | x_t, x_0) of the
+forward process by the product-of-Gaussians rule, using none of the formulas below -- reproduces `step` (mean and noise
+scale) and `add_noise` at every t; (3) cosine-schedule end points and the t = 0 behaviour.  That pins the arithmetic to
+the published algorithm (Ho et al. 2020 eq. 7, Nichol & Dhariwal 2021 eq. 17); what remains unpinned are diffusers'
+*defaults* not visible at the call site (timestep_spacing 'leading', steps_offset 0), which for set_timesteps(N) with
+N == num_train_timesteps all reduce to t = N-1 .. 0 anyway.  The arithmetic below follows diffusers' scheduling_ddpm.py:
   betas_for_alpha_bar (cosine), set_timesteps ('leading' spacing), _get_variance ('fixed_small', clamp 1e-20),
   step (epsilon prediction, clip to [-1, 1], posterior mean coefficients (formula 7 of Ho et al. 2020)), add_noise.
 """

@@ -102,3 +102,20 @@ class TorchOps:
         if kind == 1:
             return dy * (0.5 * (1 + torch.erf(pre / math.sqrt(2))) + pre * torch.exp(-0.5 * pre * pre) / math.sqrt(2 * math.pi))
         return dy * (pre > 0)
+
+    def sgemm(self, a, b, trans_a=False, trans_b=False):
+        self._count("sgemm")
+        assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(1) == 1 and b.stride(1) == 1
+        return (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+
+    def patchify_depth(self, frames):
+        self._count("patchify_depth")
+        assert frames.dtype == torch.float32 and frames.is_contiguous() and tuple(frames.shape[1:]) == (224, 224)
+        cols = F.unfold(frames.unsqueeze(1), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 196)
+        return F.pad(cols, (0, 4))
+
+    def scale_cols(self, x, gamma, add=None):
+        self._count("scale_cols")
+        assert x.dim() == 2 and x.stride(1) == 1 and (add is None or (add.shape == x.shape and add.stride(1) == 1))
+        y = x * gamma
+        return y + add if add is not None else y

@@ -167,7 +167,7 @@ def test_s2_training_forward_and_latent_query_gradient():
     ref_grad = Q.latent_query_grads(sd, cfg, ids, mask, px.float(), grids, t_s_pos, G.bfloat16().float())
     e_s, e_g = _rel(states.cpu(), ref_states), _rel(grad.cpu(), ref_grad)
     print("S2 train: states rel err", e_s, "latent_queries grad rel err", e_g)
-    assert e_s < 2e-2 and e_g < 4e-2
+    assert e_s < 2e-2 and e_g < 2e-2   # measured on B200: 6.4e-3 / 8.1e-3
     # and the states equal the inference latent plan of the same prompts (same kernels, different chunking)
     assert _rel(states, s2.generate_latents(prompts, px.cuda(), grids)) < 5e-3
 
@@ -212,7 +212,7 @@ def test_dual_system_training_step_vs_oracle():
     glat_ref = Q.latent_query_grads(s2_sd, cfg, batch["input_ids"], batch["attention_mask"], batch["pixel_values"].float(),
                                     batch["image_grid_thw"], batch["t_s_pos"], dhs_ref)
     print("train step: loss", float(loss), "oracle", float(loss_ref), "TRAJ states rel", _rel(hs.cpu(), hs_ref))
-    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 3e-2
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 1e-2   # measured on B200: 1.9e-3
     bad = []
     for k, gr in grads_ref.items():
         rel = _rel(grads[k].cpu().reshape(gr.shape), gr)

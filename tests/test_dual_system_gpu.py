@@ -56,9 +56,19 @@ def test_dual_system_step_matches_oracle_chain():
         mine_lat = model.generate_latents(prompts, px, grids)
         assert _rel(mine_lat, lat) < 2e-2
         ref = O.predict_pointgoal_action_async(s1_gpu, lat, rgb, dep, x0, nz, K=20)
-    e = _rel(traj, ref)
-    print("dual-system trajectories rel err vs oracle chain", e)
-    assert e < 4e-2
+        # reference-equivalent run: the same oracle chain in bf16 (what the reference's eager bf16 model computes)
+        s2_b = {k: v.bfloat16() for k, v in s2_gpu.items()}
+        s1_b = {k: v.bfloat16() for k, v in s1_gpu.items()}
+        lat_b, off = [], 0
+        for ids, gs in zip(prompts, gpp):
+            npb = sum(t * h * w for t, h, w in gs)
+            lat_b.append(Q.generate_latents(s2_b, cfg, torch.tensor([ids]), px[off:off + npb], gs))
+            off += npb
+        eager = O.predict_pointgoal_action_async(s1_b, torch.cat(lat_b), rgb.bfloat16(), dep.bfloat16(), x0.bfloat16(),
+                                                 nz.bfloat16(), K=20)
+    e, e_eager = _rel(traj, ref), _rel(eager, ref)
+    print("dual-system trajectories rel err vs oracle chain", e, "bf16 eager chain", e_eager)
+    assert e < 2e-2 and e < 2 * e_eager + 2e-3, (e, e_eager)
     # policy wrapper: same trajectories -> same ids as the batched tail
     pol = InternVLAN1Net(model)
     outs = pol.s1_step_latent(rgb, dep, mine_lat)
@@ -109,6 +119,6 @@ def test_training_forward_from_collated_batch():
     e_h = _rel(out.traj_hidden_states, hs)
     print("training forward: traj states rel err", e_h, "loss", float(out.loss), "oracle", float(ref))
     assert e_h < 2e-2
-    assert abs(float(out.loss) - float(ref)) / float(ref) < 3e-2
+    assert abs(float(out.loss) - float(ref)) / float(ref) < 2e-2
     with pytest.raises(ValueError):   # t_s_pos must point at the TRAJ tokens
         model.forward(noise=noise, timesteps=ts, **{**dev, "t_s_pos": [p - 1 for p in batch["t_s_pos"]]})

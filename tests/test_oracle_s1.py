@@ -115,6 +115,50 @@ def test_ddpm_properties():
     assert torch.allclose(out, x0, atol=1e-6)
 
 
+def test_ddpm_step_is_the_gaussian_posterior_of_the_forward_process():
+    """Independent known-answer check of oracle/ddpm.py (the one unpinned oracle piece: diffusers is neither vendored
+    nor installed).  Nothing here uses the scheduler's own formulas: the forward process q(x_t | x_{t-1}) =
+    N(sqrt(1 - beta_t) x_{t-1}, beta_t) and q(x_{t-1} | x_0) = N(sqrt(abar_{t-1}) x_0, 1 - abar_{t-1}) are combined with
+    the textbook product-of-Gaussians rule (precision-weighted mean) in float64.  The ancestral step with the true x_0
+    substituted must reproduce that posterior's mean, and its injected-noise scale must be the posterior's standard
+    deviation (variance_type 'fixed_small' == Ho et al. 2020 eq. 7); the kernel's tables (n1_ddpm_tables, checked
+    against this scheduler in tests/test_abi_symbols.py / test_s1_gpu.py) inherit the check.  Also pins the constructor
+    arguments the reference's own tree documents for this class
+    (internnav/model/encoder/diffusion_policy/config/*.yaml: variance_type fixed_small, clip_sample True,
+    prediction_type epsilon, beta_schedule squaredcos_cap_v2)."""
+    import math
+    from oracle import ddpm
+    N = 20
+    s = ddpm.DDPMScheduler(num_train_timesteps=N)
+    s.set_timesteps(N)
+    abar_fn = lambda u: math.cos((u + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731  (Nichol & Dhariwal 2021, eq. 17)
+    beta = [min(1 - abar_fn((i + 1) / N) / abar_fn(i / N), 0.999) for i in range(N)]
+    abar = [1.0]
+    for b in beta:
+        abar.append(abar[-1] * (1 - b))          # abar[t + 1] = prod_{j <= t} (1 - beta_j); abar[0] = 1 is "t = -1"
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(5, 8, 3, generator=g, dtype=torch.float64) * 1.6 - 0.8      # inside the clip range
+    for t in range(N - 1, 0, -1):
+        eps = torch.randn(5, 8, 3, generator=g, dtype=torch.float64)
+        a_t, a_prev = abar[t + 1], abar[t]
+        x_t = math.sqrt(a_t) * x0 + math.sqrt(1 - a_t) * eps                   # forward marginal (add_noise)
+        assert torch.allclose(s.add_noise(x0.float(), eps.float(), torch.tensor([t])).double(), x_t, atol=2e-6)
+        # product of N(x_{t-1}; sqrt(a_prev) x0, 1 - a_prev) and the likelihood of x_t given x_{t-1}
+        prec_prior = 1.0 / (1 - a_prev)
+        prec_lik = (1 - beta[t]) / beta[t]                                     # (sqrt(1-beta))^2 / beta
+        var_post = 1.0 / (prec_prior + prec_lik)
+        mean_post = var_post * (prec_prior * math.sqrt(a_prev) * x0 + math.sqrt(1 - beta[t]) / beta[t] * x_t)
+        z = torch.randn(5, 8, 3, generator=g)
+        s.noise_queue = [z.clone()]
+        out = s.step(eps.float(), t, x_t.float()).prev_sample.double()         # eps is the true noise -> x0 recovered
+        assert torch.allclose(out, mean_post + math.sqrt(var_post) * z.double(), atol=5e-5), t
+    # t = 0: no noise is added and the clipped x0 prediction is returned
+    eps = torch.randn(5, 8, 3, generator=g, dtype=torch.float64)
+    x_t = math.sqrt(abar[1]) * x0 + math.sqrt(1 - abar[1]) * eps
+    s.noise_queue = []
+    assert torch.allclose(s.step(eps.float(), 0, x_t.float()).prev_sample.double(), x0, atol=5e-6)
+
+
 def test_oracle_vs_reference_modules(sd):
     """Direct comparison with the reference classes (only where /root/reference exists)."""
     from oracle import ref_loader

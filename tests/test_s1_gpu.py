@@ -91,16 +91,26 @@ def test_sampling_loop_and_actions(env):
         eager = O.sample_trajectories(sdb, goal, rgbd, x0.bfloat16(), nz.bfloat16(), K=20)
     e, e_eager = _rel(out, ref), _rel(eager, ref)
     print("traj rel err", e, "bf16 eager", e_eager)
-    assert e < 3e-2 and e < 2 * e_eager + 2e-3, (e, e_eager)
-    # integer tail: identical trajectories -> identical ids (bit-exact); for the bf16-vs-fp32 pair report flips
+    assert e < TOL and e < 2 * e_eager + 2e-3, (e, e_eager)
+    # integer tail: identical trajectories -> identical ids (bit-exact, asserted).  Across the bf16 / fp32 pair a flip
+    # of a discrete action can only come from the trajectory difference, so it is bounded by the reference-equivalent
+    # run: our path may not flip more environments than the bf16-eager run of the oracle does (+1), and every flip is
+    # reported with its margin (distance between the two mean end points).
     from internnav_b200.postprocess import traj_to_actions
+    flips, flips_eager = [], 0
     for b in range(B):
         mine = out[b * 32:(b + 1) * 32]
         assert traj_to_actions(mine.clone()) == O.traj_to_actions(mine.clone())
-        a_ref = O.traj_to_actions(ref[b * 32:(b + 1) * 32])
-        a_out = O.traj_to_actions(mine)
+        a_ref = O.traj_to_actions(ref[b * 32:(b + 1) * 32].clone())
+        a_out = O.traj_to_actions(mine.clone())
+        a_eag = O.traj_to_actions(eager[b * 32:(b + 1) * 32].float().clone())
+        flips_eager += a_ref[:4] != a_eag[:4]
         if a_ref[:4] != a_out[:4]:
-            print("action flip from bf16 trajectory difference:", a_ref[:8], a_out[:8])
+            end_r = (ref[b * 32:(b + 1) * 32, :, :2] / 4).cumsum(1).mean(0)[-1]
+            end_o = (mine[:, :, :2].float().cpu() / 4).cumsum(1).mean(0)[-1]
+            flips.append((b, a_ref[:4], a_out[:4], float((end_r.cpu() - end_o).norm())))
+    print("action-id flips vs the fp32 oracle:", flips, "| bf16-eager flips:", flips_eager)
+    assert len(flips) <= flips_eager + 1, flips
 
 
 def test_full_s1_config2_shape(env):
@@ -117,10 +127,13 @@ def test_full_s1_config2_shape(env):
     assert out.abs().max().item() <= 1.0 + 1e-3  # last step returns the clipped x0 prediction
     with torch.no_grad():
         ref = O.sample_trajectories(sd, goal[:2].float(), rgbd[:2].float(), x0[:64], nz[:, :64], K=50)
+        eager = O.sample_trajectories(sdb, goal[:2], rgbd[:2], x0[:64].bfloat16(), nz[:, :64].bfloat16(), K=50)
     # environments are independent: the first two envs of the batched call equal a 2-env call
-    e = _rel(out[:64], ref)
-    print("cfg2 traj rel err", e)
-    assert e < 4e-2
+    e, e_eager = _rel(out[:64], ref), _rel(eager, ref)
+    print("cfg2 traj rel err", e, "bf16 eager", e_eager)
+    # 50 stochastic-sampler steps accumulate rounding: the binding bar here is the reference-equivalent one (2x the
+    # bf16-eager error); the absolute 2e-2 bar is kept for the per-stage outputs and the 20-step loop above
+    assert e < 2 * e_eager + 2e-3 and e < 4e-2, (e, e_eager)
 
 
 def test_training_branch_forward_loss(env):
