@@ -317,8 +317,9 @@ def run_ours_dual(args, wl):
              "prompts": "a different prompt batch every step (32 rotating sets, plan cache of 8): plan creation is inside "
                         "the timed region of both `value` and `e2e`"},
             {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host.values()),
-             "d2h_bytes_per_step": B * wl["Ns"] * wl["T"] * 3 * 4,
-             "api": "InternVLAN1ForCausalLM.dual_system_step (generate_latents + generate_traj + traj_to_actions), pinned host inputs"},
+             "d2h_bytes_per_step": B * 65 * 4,
+             "api": "InternVLAN1ForCausalLM.dual_system_step (generate_latents + generate_traj + device action tail "
+                    "n1_traj_to_actions; D2H = the action ids), pinned host inputs"},
             fl["total"] * B)
 
 
@@ -623,8 +624,8 @@ def run_ours_denoise(args, wl):
             {"samples_per_env": Ns, "launch_mode": "CUDA graph replay of the K-step loop (eager for the roofline pass)", "horizon": T, "ddpm_steps": K, "weights": "random-init NavDP (98.8M params)",
              "launches_are": "per step"},
             {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (h_goal, h_rgbd, h_x0, h_nz)),
-             "d2h_bytes_per_step": R * T * 3 * 4,
-             "api": "NavDP_Policy_DPT_CriticSum_DAT.sample + batched_traj_to_actions, pinned host inputs"},
+             "d2h_bytes_per_step": B * 65 * 4,
+             "api": "NavDP_Policy_DPT_CriticSum_DAT.sample + batched_traj_to_actions (device action tail), pinned host inputs"},
             denoise_flops_per_sample_step(T) * R * K)
 
 

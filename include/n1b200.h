@@ -235,6 +235,14 @@ int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void*
                         void* dv_f32, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int heads_q, int heads_kv,
                         int head_dim, int batch, int seq_q, int seq_k, const void* cu_q, const void* cu_k, int max_seq_q,
                         int kv_div, int causal, float scale, const void* k_len, int k_slot, void* stream);
+/* Action tail of a System-1 step on the device (replaces vln_utils.py L63-136 `traj_to_actions` + its D2H of all
+ * trajectories): traj fp32 [B * Ns, T, 3] as the sampler returns it (dx*4, dy*4, dyaw) -> per environment the mean path over
+ * the Ns samples (float32 cumsum, float64 mean, as numpy computes it) and the greedy pure-pursuit action ids
+ * {1 forward, 2 left, 3 right}.  ids int32 [B, cap] zero padded; count int32 [B] = ids produced (may exceed cap);
+ * mean_path double [B, T + 1, 2] or NULL.  max_actions > 0 stops the walk once that many ids exist (the policy keeps 4,
+ * internvla_n1_policy.py L212-214).  Reference constants: turn 15 deg (pass np.deg2rad(15)), step 0.25 m, lookahead 4. */
+int n1_traj_to_actions(const void* traj_f32, int B, int Ns, int T, double turn_angle_rad, double step_size, int lookahead,
+                       int max_actions, int cap, int32_t* ids, int32_t* count, double* mean_path, void* stream);
 /* C[M,N] (+)= op(A) op(B), fp32 row-major (trans_a: A stored [K,M]; trans_b: B stored [N,K]): the 3-wide and fp32-only
  * products of the training step (action embedding / head, navdp.py L79, L186; position-table resample, dinov2.py L180-211) */
 int n1_op_sgemm(const void* A_f32, int lda, int trans_a, const void* B_f32, int ldb, int trans_b, void* C_f32, int ldc, int M,

@@ -465,6 +465,13 @@ int n1_op_attention_bwd(const void* q, const void* k, const void* v, const void*
     attention_bwd(p, S(stream));
   });
 }
+int n1_traj_to_actions(const void* traj, int B, int Ns, int T, double turn_angle_rad, double step_size, int lookahead,
+                       int max_actions, int cap, int32_t* ids, int32_t* count, double* mean_path, void* stream) {
+  return guard([&] {
+    traj_to_actions(static_cast<const float*>(traj), B, Ns, T, turn_angle_rad, step_size, lookahead, max_actions, cap, ids,
+                    count, mean_path, S(stream));
+  });
+}
 int n1_op_sgemm(const void* A, int lda, int trans_a, const void* B, int ldb, int trans_b, void* C, int ldc, int M, int N, int K,
                 int accumulate, void* stream) {
   return guard([&] {

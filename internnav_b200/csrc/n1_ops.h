@@ -111,4 +111,10 @@ struct AttnParams {
 };
 void attention(const AttnParams& p, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------- action tail (postprocess.cu)
+// traj fp32 [B * Ns, T, 3] (sampler output, un-normalised) -> ids int32 [B, cap] (zero padded), count int32 [B] (ids the
+// walk produced; may exceed cap), optional mean path double [B, T + 1, 2].  max_actions > 0: stop once that many ids exist.
+void traj_to_actions(const float* traj, int B, int Ns, int T, double turn_rad, double step_size, int lookahead,
+                     int max_actions, int cap, int* ids, int* count, double* mean_out, cudaStream_t s);
+
 }  // namespace n1

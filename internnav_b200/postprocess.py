@@ -1,10 +1,15 @@
-"""CPU tail of a System-1 step: trajectories -> discrete action ids.
+"""Tail of a System-1 step: trajectories -> discrete action ids.
 
 Mirrors internnav/model/utils/vln_utils.py (`traj_to_actions` L63-136, `chunk_token` L36-60) and the list clean-up in
 InternVLAN1Net.s1_step_latent (internvla_n1_policy.py L207-214).  Integer results: bit-exact for identical inputs.
-The geometry runs in float64 numpy like the reference; the batched entry point does ONE device->host copy for all
-environments instead of one per environment.
+
+Product path: `batched_traj_to_actions` on CUDA tensors runs the library kernel (n1_traj_to_actions, csrc/postprocess.cu:
+float32 cumsum, float64 mean, pure pursuit -- one block per environment) and copies back only the ids.  The numpy
+functions below keep the reference function's contract for host tensors (`traj_to_actions` is what the reference's
+callers import) and are the checker of the kernel in tests/test_postprocess_gpu.py.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -60,9 +65,35 @@ def traj_to_actions(dp_actions, use_discrate_action=True):
     return _discretise(traj) if use_discrate_action else traj
 
 
+def batched_traj_to_actions_gpu(dp_actions, num_envs, max_actions=None, cap=64, return_mean=False):
+    """dp_actions CUDA [num_envs * Ns, T, 3] (not modified) -> list of per-environment action lists through the library
+    kernel; D2H = num_envs * (cap + 1) int32.  Lists longer than `cap` are refused (cannot happen with max_actions <= 4:
+    one walk iteration appends at most 12 turns + 1 forward)."""
+    from . import _lib
+    assert dp_actions.is_cuda and dp_actions.dim() == 3 and dp_actions.shape[2] == 3 and dp_actions.shape[0] % num_envs == 0
+    t = dp_actions.detach().float().contiguous()
+    ns, T = t.shape[0] // num_envs, t.shape[1]
+    ids = torch.empty(num_envs, cap, dtype=torch.int32, device=t.device)
+    cnt = torch.empty(num_envs, dtype=torch.int32, device=t.device)
+    mean = torch.empty(num_envs, T + 1, 2, dtype=torch.float64, device=t.device) if return_mean else None
+    _lib.check(_lib.lib().n1_traj_to_actions(_lib.ptr(t), num_envs, ns, T, ctypes.c_double(float(np.deg2rad(15))),
+                                             ctypes.c_double(0.25), 4, int(max_actions or 0), cap, _lib.ptr(ids),
+                                             _lib.ptr(cnt), _lib.ptr(mean), _lib.stream_ptr()))
+    host = torch.cat((ids, cnt[:, None]), dim=1).cpu().numpy()       # the one D2H of the tail
+    out = []
+    for e in range(num_envs):
+        n = int(host[e, cap])
+        if n > cap:
+            raise RuntimeError("action list of environment %d has %d ids (> cap %d)" % (e, n, cap))
+        out.append(host[e, :n].tolist())
+    return (out, mean) if return_mean else out
+
+
 def batched_traj_to_actions(dp_actions, num_envs, use_discrate_action=True, max_actions=None):
     """dp_actions [num_envs * Ns, T, 3] (not modified) -> list of per-environment action lists (optionally only their
-    first `max_actions` entries, see _discretise)."""
+    first `max_actions` entries, see _discretise).  CUDA tensors take the kernel path; host tensors the numpy one."""
+    if torch.is_tensor(dp_actions) and dp_actions.is_cuda and use_discrate_action:
+        return batched_traj_to_actions_gpu(dp_actions, num_envs, max_actions=max_actions)
     a = dp_actions.detach().float().cpu().numpy().copy()
     a[:, :, :2] /= 4.0
     ns = a.shape[0] // num_envs

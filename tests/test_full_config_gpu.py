@@ -7,7 +7,10 @@
   (iii) two host threads drive the same handles concurrently (S2 on one stream / workspace, S1 on another), as the
         reference agent does (internvla_n1_agent.py L133-208), and reproduce the single-threaded results bit for bit.
 
-Tolerance: rel-L2 vs the fp32 oracle <= 2e-2 and <= 2x the bf16-eager error (+ 2e-3 slack)."""
+Tolerance: rel-L2 vs the fp32 oracle <= 2x the bf16-eager error (+ 2e-3 slack) and <= 2e-2 -- except
+that at FULL DEPTH with random weights the reference-equivalent bf16-eager run itself sits at 2.1e-2 (latents) / 2.7e-2
+(vision tower), i.e. above the absolute bar, so there the absolute bar is 3e-2 and the binding requirement is that the
+CUDA path is at least as accurate as bf16 eager (measured on B200: 2.26e-2 vs 2.72e-2, 1.88e-2 vs 2.14e-2)."""
 import threading
 
 import numpy as np
@@ -66,8 +69,10 @@ def test_full_depth_one_env_vs_fp32_oracle(full):
     e_l, ee_l = _rel(lat[0], ref_l[0]), _rel(eag_l[0], ref_l[0])
     print("full depth (32 + 28 layers, S = 304): ViT rel err %.4f (bf16 eager %.4f); latents rel err %.4f (bf16 eager %.4f)"
           % (e_v, ee_v, e_l, ee_l))
-    assert e_v < TOL and e_v < 2 * ee_v + 2e-3, (e_v, ee_v)
-    assert e_l < TOL and e_l < 2 * ee_l + 2e-3, (e_l, ee_l)
+    # 60 bf16 layers deep: the absolute bar is 3e-2 (see the module docstring); the binding bar is "no worse than the
+    # reference-equivalent bf16-eager run"
+    assert e_v < 3e-2 and e_v < ee_v + 2e-3, (e_v, ee_v)
+    assert e_l < 3e-2 and e_l < ee_l + 2e-3, (e_l, ee_l)
 
 
 def test_batch64_equals_64_single_env_calls_system2(full):
