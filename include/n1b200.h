@@ -282,6 +282,12 @@ int n1_op_gemm_row384(const void* A_bf16, int lda, const void* W_bf16, int ldw, 
 int n1_op_fused_mlp(const void* x_bf16, int ldx, const void* w1_bf16, const float* b1, const void* w2_bf16,
                     const float* b2, const void* residual_bf16, int ldr, void* out_bf16, int ldo, int M, int cluster,
                     void* stream);
+/* NavDP decoder FF block with its LayerNorm, residual stream resident in tensor memory (ff_block.cu):
+ * out = x + W2 GELU(W1 LayerNorm(x; ln_w, ln_b, eps) + b1) + b2 -- norm3 / linear1 / GELU / linear2 / residual of
+ * nn.TransformerDecoderLayer(norm_first=True), navdp.py L57-66.  x, out bf16 [M, 384] (may alias).  cluster: 1 or 2. */
+int n1_op_ff_block(const void* x_bf16, int ldx, const float* ln_w, const float* ln_b, float eps, const void* w1_bf16,
+                   const float* b1, const void* w2_bf16, const float* b2, void* out_bf16, int ldo, int M, int cluster,
+                   void* stream);
 /* weight-streaming GEMM for M <= 64 rows (decode passes): out bf16 [M, N or N/2 for SwiGLU]; bias fp32 [N] / residual
  * bf16 [M, ldr] may be NULL; act: 0 none, 1 GELU, 2 ReLU, 3 SwiGLU; ws: n1_op_gemm_skinny_workspace_bytes() of scratch */
 size_t n1_op_gemm_skinny_workspace_bytes(void);

@@ -66,6 +66,8 @@ SYMBOLS = {
                                   c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     "n1_op_fused_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                 c_int, c_int, c_void_p]),
+    "n1_op_ff_block": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_void_p]),
     "n1_op_gemm_skinny_workspace_bytes": (c_size_t, []),
     "n1_op_gemm_skinny": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -199,6 +201,17 @@ def fused_mlp(x, w1, b1, w2, b2, residual=None, out=None, cluster=2):
                                 c_void_p(residual.data_ptr()) if residual is not None else None,
                                 residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
                                 out.stride(0), x.shape[0], cluster, stream_ptr()))
+    return out
+
+
+def ff_block(x, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, out=None, cluster=2):
+    """out = x + gelu(LayerNorm(x) @ w1.T + b1) @ w2.T + b2 (NavDP decoder FF block, residual stream in tensor memory)."""
+    assert x.dtype == torch.bfloat16 and x.shape[1] == 384 and w1.shape == (1536, 384) and w2.shape == (384, 1536)
+    assert w1.is_contiguous() and w2.is_contiguous() and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape[0], 384, device=x.device, dtype=torch.bfloat16)
+    check(lib().n1_op_ff_block(c_void_p(x.data_ptr()), x.stride(0), ptr(ln_w), ptr(ln_b), eps, ptr(w1), ptr(b1), ptr(w2),
+                               ptr(b2), c_void_p(out.data_ptr()), out.stride(0), x.shape[0], cluster, stream_ptr()))
     return out
 
 

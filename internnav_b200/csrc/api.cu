@@ -567,6 +567,13 @@ int n1_op_fused_mlp(const void* x, int ldx, const void* w1, const float* b1, con
   });
 }
 
+int n1_op_ff_block(const void* x, int ldx, const float* ln_w, const float* ln_b, float eps, const void* w1, const float* b1,
+                   const void* w2, const float* b2, void* out, int ldo, int M, int cluster, void* stream) {
+  return guard([&] {
+    ff_block_384(B16(x), ldx, ln_w, ln_b, eps, B16(w1), b1, B16(w2), b2, B16(out), ldo, M, cluster, S(stream));
+  });
+}
+
 size_t n1_op_gemm_skinny_workspace_bytes(void) { return gemm_skinny_workspace_bytes(); }
 int n1_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
                       const void* bias, const void* residual, int ldr, int act, void* ws, size_t ws_bytes, void* stream) {

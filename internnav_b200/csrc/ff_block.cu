@@ -1,0 +1,448 @@
+// FF block of the NavDP decoder layer as ONE kernel, residual stream resident in tensor memory:
+//
+//     x  <-  x + W2 · GELU(W1 · LayerNorm(x) + b1) + b2            (D = 384, F = 1536; navdp.py L57-66: norm3 / linear1 /
+//                                                                    exact GELU / linear2 / residual of the pre-norm layer)
+//
+// replaces three launches (LayerNorm, FF1+GELU GEMM, FF2+residual GEMM) and the HBM round trips of the [rows, 384]
+// normalised input and the [rows, 1536] hidden.  Per CTA, one 128-row tile at a time (persistent over tiles):
+//
+//   prologue (16 epilogue warps, thread = one row x 96 columns): x rows from global -> LayerNorm -> bf16 A operand in SMEM
+//       (128-byte swizzled K-major, 96 KB) AND  x + b2  in fp32 into TMEM columns 0..383 (tcgen05.st): the second GEMM
+//       then ACCUMULATES into the residual stream, so the residual add and the output bias cost no epilogue work;
+//   hidden chunks of 64 columns:  H_j = LN(x) · W1[64j:64j+64]^T  (tcgen05.mma M128 N64 into TMEM 384 + 64 (j & 1))
+//       -> 8 of the 16 epilogue warps (group j & 1): tcgen05.ld, + b1, GELU (packed f32x2 polynomial, no MUFU), bf16,
+//          swizzled SMEM chunk  ->  x_tmem += H_j · W2[:, 64j:64j+64]^T   (2 x M128 N192 per k-step);
+//   W1 / W2 slices stream through a 4 x 24 KB TMA ring; CM = 2: the two CTAs of a cluster fetch half a slice each and
+//       multicast it (halves the L2 -> SMEM weight traffic, the limiter of this short-K shape);
+//   final epilogue: TMEM 0..383 -> bf16 -> SMEM staging -> TMA store to x (in place).
+//
+// Differences from the first fused MLP (fused_mlp.cu, kept for reference): LayerNorm inside, residual in TMEM, 16
+// epilogue warps instead of 8 (the GELU epilogue was the limiter: 2 warps per scheduler could not hide FMA latency), and
+// a MUFU-free GELU in packed fp32.
+#include <mutex>
+
+#include "n1_ops.h"
+#include "n1_ptx.cuh"
+
+namespace n1 {
+namespace {
+
+constexpr int D = 384, F = 1536, BM = 128, HC = 64;
+constexpr int NCH = F / HC;                          // 24 hidden chunks
+constexpr int kSlots = 4, kSlotBytes = 24576;
+constexpr int kLag = 2;                              // GEMM2(j) is issued after GEMM1(j + kLag)
+constexpr int kABytes = BM * D * 2;                  // 98304: 6 k-blocks of [128 x 64]
+constexpr int kHBytes = BM * HC * 2;                 // 16384 per buffer
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 32 * kEpiWarps;        // 576
+constexpr int kStatBytes = 128 * 2 * 4;              // LayerNorm statistics of the tile: [128 rows][mean, rstd]
+constexpr int kSmem = kABytes + 2 * kHBytes + kSlots * kSlotBytes + kStatBytes + 512 + 1024;
+
+struct FfArgs {
+  int M;
+  int tiles_m;
+  const bf16* x;   // [M, ldx] residual stream in
+  int ldx;
+  const float* ln_w;
+  const float* ln_b;
+  float eps;
+  const float* b1;
+  const float* b2;
+};
+
+// erf(u / sqrt 2) ~= u P(u^2) on |u| <= 4 (least-squares fit weighted for the GELU product, |gelu error| <= 2.0e-4,
+// i.e. a fraction of a bf16 ulp of the result; the clamp makes it exactly +-1 beyond).  Two values per instruction.
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 u = make_float2(fminf(fmaxf(x.x, -4.0f), 4.0f), fminf(fmaxf(x.y, -4.0f), 4.0f));
+  const float2 s = __fmul2_rn(u, u);
+  float2 p = __ffma2_rn(make_float2(4.4781046e-08f, 4.4781046e-08f), s, make_float2(-3.156104e-06f, -3.156104e-06f));
+  p = __ffma2_rn(p, s, make_float2(9.50805e-05f, 9.50805e-05f));
+  p = __ffma2_rn(p, s, make_float2(-0.0016200024f, -0.0016200024f));
+  p = __ffma2_rn(p, s, make_float2(0.017507503f, 0.017507503f));
+  p = __ffma2_rn(p, s, make_float2(-0.12907527f, -0.12907527f));
+  p = __ffma2_rn(p, s, make_float2(0.7957365f, 0.7957365f));
+  float2 e = __fmul2_rn(u, p);
+  e = make_float2(fminf(fmaxf(e.x, -1.0f), 1.0f), fminf(fmaxf(e.y, -1.0f), 1.0f));
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(h, e, h);
+}
+
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// barrier among the 16 epilogue warps only (named barrier 1; warps 0 and 1 never join it)
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+template <int CM>
+__global__ void __launch_bounds__(kThreads, 1)
+ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmOut, const FfArgs args) {
+  constexpr uint16_t kMask = (1u << CM) - 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sH = smem + kABytes;
+  uint8_t* sW = sH + 2 * kHBytes;
+  float* sStat = reinterpret_cast<float*>(sW + kSlots * kSlotBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kSlots * kSlotBytes + kStatBytes);
+  uint64_t* w_full = bars;                 // [4]
+  uint64_t* w_empty = bars + 4;            // [4]
+  uint64_t* a_full = bars + 8;             // LN(x) operand written and x + b2 seeded in TMEM (16 warp arrivals)
+  uint64_t* hacc_full = bars + 10;         // [2] GEMM1(j) complete -> TMEM H readable
+  uint64_t* hacc_empty = bars + 12;        // [2] epilogue group finished reading TMEM H (8 warp arrivals)
+  uint64_t* hs_full = bars + 14;           // [2] SMEM H written (8 warp arrivals)
+  uint64_t* hs_empty = bars + 16;          // [2] GEMM2 finished reading SMEM H
+  uint64_t* y_full = bars + 18;            // all MMAs of the tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CM > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
+  const int super_m = (args.tiles_m + CM - 1) / CM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1), tma_prefetch_desc(&tmW2), tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < kSlots; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], CM);
+    mbar_init(a_full, kEpiWarps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hacc_full[b], 1), mbar_init(&hacc_empty[b], 8);
+      mbar_init(&hs_full[b], 8), mbar_init(&hs_empty[b], 1);
+    }
+    mbar_init(y_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  if (CM > 1) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (weights only)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t wphase = 0;
+      auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
+      for (int t = cluster_id; t < super_m; t += num_clusters) {
+        for (int j = 0; j < NCH + kLag; ++j) {
+          if (j < NCH) {  // W1 rows [64j, 64j+64): two half-slices of 3 k-blocks
+            for (int hf = 0; hf < 2; ++hf) {
+              mbar_wait(&w_empty[slot], wphase ^ 1);
+              mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
+              uint8_t* dst = sW + slot * kSlotBytes;
+              for (int kb = 0; kb < 3; ++kb) {
+                if (CM == 1) {
+                  tma_load_2d(dst + kb * 8192, &tmW1, &w_full[slot], (hf * 3 + kb) * 64, j * HC);
+                } else {  // each CTA fetches 32 of the 64 rows and multicasts them
+                  tma_load_2d_mc(dst + kb * 8192 + rank * 4096, &tmW1, &w_full[slot], (hf * 3 + kb) * 64,
+                                 j * HC + rank * 32, kMask);
+                }
+              }
+              next();
+            }
+          }
+          if (j >= kLag) {  // W2[:, 64(j-kLag) : +64): two N-halves of 192 rows
+            for (int nh = 0; nh < 2; ++nh) {
+              mbar_wait(&w_empty[slot], wphase ^ 1);
+              mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
+              uint8_t* dst = sW + slot * kSlotBytes;
+              if (CM == 1) {
+                tma_load_2d(dst, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192);
+              } else {
+                tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192 + rank * 96, kMask);
+              }
+              next();
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 192);
+      int slot = 0;
+      uint32_t wphase = 0, tphase = 0;
+      uint32_t hacc_ph[2] = {0, 0}, hs_ph[2] = {0, 0};
+      auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
+      auto release = [&](uint64_t* bar) { if (CM == 1) umma_commit(bar); else umma_commit_mc(bar, kMask); };
+      for (int t = cluster_id; t < super_m; t += num_clusters) {
+        mbar_wait(a_full, tphase);   // LN(x) in SMEM, x + b2 in TMEM columns 0..383
+        tc_fence_after();
+        for (int j = 0; j < NCH + kLag; ++j) {
+          if (j < NCH) {
+            const int b = j & 1;
+            mbar_wait(&hacc_empty[b], hacc_ph[b] ^ 1);  // epilogue done with the previous use of TMEM H[b]
+            tc_fence_after();
+            for (int hf = 0; hf < 2; ++hf) {
+              mbar_wait(&w_full[slot], wphase);
+              tc_fence_after();
+#pragma unroll
+              for (int kb = 0; kb < 3; ++kb) {
+                const uint64_t ad = umma_desc_sw128(smem_u32(sA + (hf * 3 + kb) * 16384));
+                const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes + kb * 8192));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem + 384 + b * HC, ad + 2 * k, bd + 2 * k, idesc1, (hf | kb | k) != 0 ? 1u : 0u);
+              }
+              release(&w_empty[slot]);
+              next();
+            }
+            umma_commit(&hacc_full[b]);
+            hacc_ph[b] ^= 1;
+          }
+          if (j >= kLag) {  // GEMM2 trails GEMM1 by kLag chunks so the tensor pipe has work while GELU(H) is produced
+            const int jj = j - kLag, b = jj & 1;
+            mbar_wait(&hs_full[b], hs_ph[b]);  // GELU(H_jj) is in shared memory
+            hs_ph[b] ^= 1;
+            tc_fence_after();
+            const uint64_t ad = umma_desc_sw128(smem_u32(sH + b * kHBytes));
+            for (int nh = 0; nh < 2; ++nh) {
+              mbar_wait(&w_full[slot], wphase);
+              tc_fence_after();
+              const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem + nh * 192, ad + 2 * k, bd + 2 * k, idesc2, 1u);  // accumulates onto x + b2
+              release(&w_empty[slot]);
+              next();
+            }
+            umma_commit(&hs_empty[b]);
+          }
+        }
+        umma_commit(y_full);
+        tphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ 16 epilogue warps
+    const int ew = warp - 2;                 // 0..15
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int sub = ew >> 2;                 // 0..3: which of the 4 warps of this quarter
+    const int grp = sub & 1, colhalf = sub >> 1;   // GELU: hidden-chunk group (= H buffer) and 32-column half
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    uint32_t hacc_phase = 0, hs_phase = 0, tphase = 0;
+    // bulk-store staging: 2 KB per warp inside the H buffers (idle between the tile's last GEMM2 and the next tile's first
+    // GELU write); all 16 warps pass epi_barrier() in the next prologue after draining their store reads, so no warp's
+    // GELU write can land on another warp's pending store
+    uint8_t* my_store = sH + ew * 2048;
+    for (int t = cluster_id; t < super_m; t += num_clusters) {
+      const int tm = t * CM + rank;
+      const int row = tm * BM + r_in_tile;
+      const bool row_ok = row < args.M;
+      // ---- prologue, pass A: row statistics, one warp per row (8 rows per warp), coalesced 8-byte loads, two-pass variance
+      for (int rr = 0; rr < 8; ++rr) {
+        const int rt = ew * 8 + rr;
+        const long grow = (long)tm * BM + rt;
+        float v[12];
+        float s = 0.f;
+        if (grow < args.M) {
+          const bf16* xr = args.x + grow * args.ldx;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(xr + (lane + i * 32) * 4));
+            v[i * 4 + 0] = bf16_lo(q.x), v[i * 4 + 1] = bf16_hi(q.x), v[i * 4 + 2] = bf16_lo(q.y), v[i * 4 + 3] = bf16_hi(q.y);
+            s += v[i * 4] + v[i * 4 + 1] + v[i * 4 + 2] + v[i * 4 + 3];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) v[i] = 0.f;
+        }
+        const float mu = warp_sum(s) * (1.0f / D);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sq += (v[i] - mu) * (v[i] - mu);
+        const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + args.eps);
+        if (lane == 0) sStat[rt * 2] = mu, sStat[rt * 2 + 1] = rs;
+      }
+      epi_barrier();
+      // ---- pass B: this thread's row, columns [sub * 96, sub * 96 + 96)
+      const float mean = sStat[r_in_tile * 2], rstd = sStat[r_in_tile * 2 + 1];
+      const bf16* xrow = args.x + (long)row * args.ldx + sub * 96;
+      // normalised row -> swizzled A operand; x + b2 -> TMEM (fp32) in three batches of 32 columns
+#pragma unroll
+      for (int batch = 0; batch < 3; ++batch) {
+        uint32_t seed[32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = sub * 96 + batch * 32 + i * 8;
+          const uint4 q = row_ok ? __ldg(reinterpret_cast<const uint4*>(xrow + batch * 32 + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+          const float4 lw0 = __ldg(reinterpret_cast<const float4*>(args.ln_w + col));
+          const float4 lw1 = __ldg(reinterpret_cast<const float4*>(args.ln_w + col + 4));
+          const float4 lb0 = __ldg(reinterpret_cast<const float4*>(args.ln_b + col));
+          const float4 lb1 = __ldg(reinterpret_cast<const float4*>(args.ln_b + col + 4));
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(args.b2 + col));
+          const float4 c1 = __ldg(reinterpret_cast<const float4*>(args.b2 + col + 4));
+          const float lw[8] = {lw0.x, lw0.y, lw0.z, lw0.w, lw1.x, lw1.y, lw1.z, lw1.w};
+          const float lb[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+          const float cb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          float v[8], y[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[2 * e] = bf16_lo(w4[e]), v[2 * e + 1] = bf16_hi(w4[e]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            y[e] = (v[e] - mean) * rstd * lw[e] + lb[e];
+            seed[i * 8 + e] = __float_as_uint(v[e] + cb[e]);
+          }
+          // K-major, 128-byte swizzle: k-block col / 64, 16-byte chunk (col % 64) / 8 at position chunk ^ (row % 8)
+          const int kb = col >> 6, ch = (col & 63) >> 3;
+          uint8_t* dst = sA + kb * 16384 + (r_in_tile >> 3) * 1024 + (r_in_tile & 7) * 128 + ((ch ^ (r_in_tile & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
+                                                      pack_bf16(y[6], y[7]));
+        }
+        tmem_st32(tmem + lane_base + sub * 96 + batch * 32, seed);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+
+      // ---- hidden chunks: group `grp` (8 warps) owns the chunks j = grp, grp + 2, ...; this warp its 32-column half
+      for (int j = grp; j < NCH; j += 2) {
+        const int b = grp;
+        mbar_wait(&hacc_full[b], hacc_phase);
+        hacc_phase ^= 1;
+        tc_fence_after();
+        uint32_t r0[32];
+        tmem_ld32(tmem + lane_base + 384 + b * HC + colhalf * 32, r0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hacc_empty[b]);
+        const float* bias = args.b1 + j * HC + colhalf * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+          const float2 g0 = gelu2(make_float2(__uint_as_float(r0[c]) + bb.x, __uint_as_float(r0[c + 1]) + bb.y));
+          const float2 g1 = gelu2(make_float2(__uint_as_float(r0[c + 2]) + bb.z, __uint_as_float(r0[c + 3]) + bb.w));
+          pk[c / 2] = pack_bf16(g0.x, g0.y), pk[c / 2 + 1] = pack_bf16(g1.x, g1.y);
+        }
+        mbar_wait(&hs_empty[b], hs_phase ^ 1);  // GEMM2(j - 2) has finished reading this buffer
+        hs_phase ^= 1;
+        uint8_t* rowp = sH + b * kHBytes + (r_in_tile >> 3) * 1024 + (r_in_tile & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int ch = colhalf * 4 + c;
+          *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_in_tile & 7)) << 4)) =
+              make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hs_full[b]);
+      }
+      // ---- final epilogue: TMEM columns 0..383 already hold x + b2 + FF(LN(x)); 3 chunks of 32 columns per warp
+      mbar_wait(y_full, tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = sub; chunk < D / 32; chunk += 4) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem + lane_base + chunk * 32, r);
+        tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; c += 8)
+          *reinterpret_cast<uint4*>(my_store + lane * 64 + c * 2) =
+              make_uint4(pack_bf16(__uint_as_float(r[c]), __uint_as_float(r[c + 1])),
+                         pack_bf16(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])),
+                         pack_bf16(__uint_as_float(r[c + 4]), __uint_as_float(r[c + 5])),
+                         pack_bf16(__uint_as_float(r[c + 6]), __uint_as_float(r[c + 7])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, my_store, chunk * 32, tm * BM + quarter * 32);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) tma_store_wait_read<0>();  // the staging area is the next tile's H buffer
+      __syncwarp();
+      tphase ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  if (CM > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int CM>
+void launch_ff(const bf16* w1, const bf16* w2, const FfArgs& a, bf16* out, int ldo, cudaStream_t stream) {
+  static std::once_flag once;
+  static int max_clusters = 0;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(ff_block_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    max_clusters = device_sm_count() / CM;
+    if (CM > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(device_sm_count() / CM * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmem;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+      cfg.attrs = &at, cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, ff_block_kernel<CM>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    }
+  });
+  CUtensorMap tmW1 = tma_map_2d(w1, F, D, D, HC / CM, 64, true);
+  CUtensorMap tmW2 = tma_map_2d(w2, D, F, F, 192 / CM, 64, true);
+  CUtensorMap tmOut = tma_map_2d(out, a.M, D, ldo, 32, 32, false);
+  const int super_m = (a.tiles_m + CM - 1) / CM;
+  const int clusters = super_m < max_clusters ? super_m : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmem, cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+  cfg.attrs = &at, cfg.numAttrs = 1;
+  N1_CUDA(cudaLaunchKernelEx(&cfg, ff_block_kernel<CM>, tmW1, tmW2, tmOut, a));
+  prof_count_gemm(4.0 * a.M * (double)D * F);
+  N1_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+// x [M, ldx] bf16 residual stream (read), out [M, ldo] bf16 (written; may alias x); w1 [1536, 384], w2 [384, 1536] bf16
+// contiguous; ln_w / ln_b / b2 fp32 [384], b1 fp32 [1536].  out = x + W2 GELU(W1 LN(x) + b1) + b2.
+void ff_block_384(const bf16* x, int ldx, const float* ln_w, const float* ln_b, float eps, const bf16* w1, const float* b1,
+                  const bf16* w2, const float* b2, bf16* out, int ldo, int M, int cluster, cudaStream_t stream) {
+  if (M <= 0) return;
+  N1_CHECK(x && out && w1 && w2 && ln_w && ln_b && b1 && b2, "ff_block_384: null pointer");
+  N1_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ldx % 8 == 0, "ff_block_384: misaligned x");
+  FfArgs a;
+  a.M = M, a.tiles_m = (M + BM - 1) / BM;
+  a.x = x, a.ldx = ldx, a.ln_w = ln_w, a.ln_b = ln_b, a.eps = eps, a.b1 = b1, a.b2 = b2;
+  if (cluster >= 2 && a.tiles_m >= 2)
+    launch_ff<2>(w1, w2, a, out, ldo, stream);
+  else
+    launch_ff<1>(w1, w2, a, out, ldo, stream);
+}
+
+}  // namespace n1

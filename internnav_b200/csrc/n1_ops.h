@@ -111,6 +111,12 @@ struct AttnParams {
 };
 void attention(const AttnParams& p, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------- fused decoder blocks
+// FF block of the NavDP decoder layer in one kernel (ff_block.cu): out = x + W2 GELU(W1 LayerNorm(x) + b1) + b2 with the
+// residual stream held in tensor memory.  x / out bf16 [M, ld] (may alias), w1 [1536, 384], w2 [384, 1536] contiguous.
+void ff_block_384(const bf16* x, int ldx, const float* ln_w, const float* ln_b, float eps, const bf16* w1, const float* b1,
+                  const bf16* w2, const float* b2, bf16* out, int ldo, int M, int cluster, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------- action tail (postprocess.cu)
 // traj fp32 [B * Ns, T, 3] (sampler output, un-normalised) -> ids int32 [B, cap] (zero padded), count int32 [B] (ids the
 // walk produced; may exceed cap), optional mean path double [B, T + 1, 2].  max_actions > 0: stop once that many ids exist.

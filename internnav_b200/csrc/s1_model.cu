@@ -48,6 +48,16 @@ int row384_mode() {
 // N1_FUSED_MLP: 0 (default) = two GEMMs, 1 = fused kernel, 2 = fused kernel with 2-CTA weight multicast.
 // The fused kernel (fused_mlp.cu) is EXPERIMENTAL and off: it is correct when it completes, but it is slower than the
 // two-GEMM path (GELU issue-bound, ~400 vs ~320 us at 65536 rows) and a rare hang was seen under pytest on B200.
+// N1_FF_BLOCK: 0 = off (LayerNorm + FF1 + FF2 as three kernels), 1 / 2 = the FF-block kernel (cluster size)
+int ff_block_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("N1_FF_BLOCK");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
 int fused_mlp_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -469,10 +479,14 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     pc.heads_q = pc.heads_kv = dims.heads, pc.hd = 48, pc.batch = B * Ns, pc.seq_q = T, pc.seq_k = Mtok;
     pc.kv_div = Ns, pc.scale = scale48;
     attention(pc, s);
-    res_gemm_ln(L.ca_out, d.att, D, &L.n3);
+    const bool ffb = ff_block_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536;
+    res_gemm_ln(L.ca_out, d.att, D, ffb ? nullptr : &L.n3);  // the FF-block kernel applies norm3 itself
 
     const LNp* next_ln = l + 1 < dims.layers ? &dec_[l + 1].n1 : nullptr;  // the head applies the final LayerNorm itself
-    if (fused_mlp_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536) {
+    if (ffb) {
+      ff_block_384(xc, D, L.n3.w, L.n3.b, 1e-5f, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, xc, D, (int)R, ff_block_mode(), s);
+      if (next_ln) layernorm(xc, D, d.ln, D, next_ln->w, next_ln->b, (int)R, D, 1e-5f, 0, s);
+    } else if (fused_mlp_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536) {
       fused_mlp_384(d.ln, D, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, xc, D, xc, D, (int)R, fused_mlp_mode(), s);
       if (next_ln) layernorm(xc, D, d.ln, D, next_ln->w, next_ln->b, (int)R, D, 1e-5f, 0, s);
     } else {

@@ -218,6 +218,32 @@ def test_fused_mlp(L, M, cluster):
     assert _rel(r2, ref) < 8e-3
 
 
+
+@pytest.mark.parametrize("M,cluster", [(128, 1), (1000, 1), (256, 2), (1000, 2), (65536 // 8, 2), (300, 2), (65536, 2)])
+def test_ff_block(L, M, cluster):
+    """FF block of the NavDP decoder layer in one kernel (ff_block.cu): LayerNorm + linear1 + GELU + linear2 + residual,
+    residual stream in tensor memory; against fp32 PyTorch on the same bf16 inputs."""
+    torch.manual_seed(M + cluster)
+    x = (torch.randn(M, 384, device="cuda") * 1.5 + 0.3).bfloat16()
+    w1 = (torch.randn(1536, 384, device="cuda") / math.sqrt(384)).bfloat16()
+    w2 = (torch.randn(384, 1536, device="cuda") / math.sqrt(1536)).bfloat16()
+    b1, b2 = torch.randn(1536, device="cuda") * 0.1, torch.randn(384, device="cuda") * 0.1
+    lw, lb = 1 + 0.1 * torch.randn(384, device="cuda"), 0.1 * torch.randn(384, device="cuda")
+    h = torch.nn.functional.layer_norm(x.float(), (384,), lw, lb, 1e-5).bfloat16().float()   # the kernel's operand is bf16
+    ref = x.float() + torch.nn.functional.gelu(h @ w1.float().T + b1) @ w2.float().T + b2
+    out = L.ff_block(x, lw, lb, w1, b1, w2, b2, cluster=cluster)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    # in place on the residual stream, as the decoder uses it; twice in a row (persistent state must not leak)
+    r2 = x.clone()
+    L.ff_block(r2, lw, lb, w1, b1, w2, b2, out=r2, cluster=cluster)
+    assert torch.equal(r2, out)
+    # the unfused kernels of the library compute the same block (LayerNorm -> GEMM+GELU -> GEMM+residual)
+    hk = L.layernorm(x, lw, lb, 1e-5)
+    hid = L.gemm(hk, w1, bias=b1, act=L.ACT_GELU)
+    un = L.gemm(hid, w2, bias=b2, residual=x)
+    assert _rel(out, un) < 6e-3, _rel(out, un)
+
 @pytest.mark.parametrize("M,K,use_ln,use_gamma", [(128, 384, False, False), (300, 384, True, True), (1000, 1536, True, False),
                                                   (4096, 384, True, False)])
 def test_gemm_row384(L, M, K, use_ln, use_gamma):
