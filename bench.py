@@ -144,6 +144,40 @@ def dual_flops_per_env(wl):
     return dict(llm=llm, vit=vit, rgbd=vits, denoise=den, total=llm + vit + vits + den)
 
 
+def _gemm_classes(shapes, wl, world_B):
+    """Group the event-timed GEMM launches of one step by stage.  Rule: by the contraction / output widths of the model
+    (decoder 3584 / 18944, vision tower 1280 / 3420 / 5120 / 1176, System 1 384-wide)."""
+    def cls(sh):
+        M, N, K = sh["M"], abs(sh["N"]), sh["K"]
+        if N == 896 and K == 3584:
+            return "s1_other"
+        if K in (3584, 18944) or N in (3584, 37888, 4608) and K == 3584:
+            return "llm"
+        if K in (1280, 1176, 1184, 3424, 5120) or N in (1280, 3840, 6848, 5120):
+            return "vit"
+        if M == world_B * wl.get("Ns", 32) * wl.get("T", 32):
+            return "denoiser"
+        return "s1_other"
+    out = {}
+    for sh in shapes:
+        c = out.setdefault(cls(sh), {"launches": 0, "ms": 0.0, "tflop": 0.0})
+        fl = (4.0 if sh["N"] < 0 else 2.0) * sh["M"] * abs(sh["N"]) * sh["K"] * sh["count"]
+        c["launches"] += sh["count"]
+        c["ms"] += sh["ms"]
+        c["tflop"] += fl / 1e12
+    return out
+
+
+def _traffic_table():
+    """ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of named GEMM shapes, from committed captures
+    (profiles/r2_gemm_traffic.json: {"MxNxK": {"bytes": ..., "source": "profiles/..."}}); absent -> traffic null."""
+    p = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return {}
+
+
 def build_dual(dev, wl, rank):
     """Random-init InternVLA-N1 (Qwen2.5-VL-7B shapes + NavDP) and one step's synthetic inputs."""
     import numpy as np
@@ -186,7 +220,8 @@ def run_ours(args, wl):
 
 
 def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, extra_cfg, e2e_info, algo_flops_step,
-            unit="policy-steps/s", metric="InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", extra_top=None):
+            unit="policy-steps/s", metric="InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", extra_top=None,
+            shapes=None, stage_ms=None):
     import torch.distributed as dist
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -215,9 +250,43 @@ def _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B, e
                      "gemm_launches_per_step": int(prof["gemm_launches"]), "gemm_ms_per_step": prof["gemm_ms"],
                      "gemm_share_of_step": prof["gemm_ms"] / ms_per_step},
     }
+    if shapes:
+        # the single dominant kernel launch shape of the step (by summed time) carries the headline roofline entry; the
+        # family sum stays as `gemm_family`; `roofline_classes` gives TFLOP / ms / fraction per stage
+        dom = max(shapes, key=lambda sh: sh["ms"])
+        fl = (4.0 if dom["N"] < 0 else 2.0) * dom["M"] * abs(dom["N"]) * dom["K"]
+        per_ms = dom["ms"] / dom["count"]
+        key = "%dx%dx%d" % (dom["M"], abs(dom["N"]), dom["K"])
+        tr = _traffic_table().get(key)
+        fam = dict(out["roofline"])
+        a_tf = fl / (per_ms * 1e-3) / 1e12
+        pk1 = pk["tf"]   # a single launch is short: the burst figure is the denominator
+        out["roofline"] = {"bound": "tensor", "kernel": "n1::gemm_kernel<BN,CM> (tcgen05) M x N x K = %s, %d launches per step"
+                                                         % (key, dom["count"]),
+                           "achieved": a_tf, "peak": pk1, "unit": "TFLOP/s", "frac": a_tf / pk1,
+                           "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                           "algorithmic_bytes": 2.0 * (dom["M"] * dom["K"] + abs(dom["N"]) * dom["K"] + dom["M"] * abs(dom["N"])
+                                                       // (2 if abs(dom["N"]) == 37888 else 1)),
+                           "us_per_launch": per_ms * 1e3, "ms_per_step": dom["ms"],
+                           "peak_source": pk["src"] + " burst (single launch)", "gemm_family": fam}
+        cl = _gemm_classes(shapes, wl, B)
+        for c in cl.values():
+            c["tflops"] = c["tflop"] / (c["ms"] * 1e-3) if c["ms"] > 0 else 0.0
+            c["frac_of_sustained_peak"] = c["tflops"] / pk["tf_sustained"]
+        out["roofline_classes"] = cl
+    if stage_ms:
+        out["stage_ms"] = stage_ms
     if extra_top:
         out.update(extra_top)
     if rank == 0:
+        if world == 1 and not args.no_eager_baseline and wl["kind"] == "dual":
+            # same-GPU, same-batch PyTorch-eager baseline (cuBLAS + SDPA), measured after our arm in this process:
+            # separates "batching" from "kernels" in the speed-up (north_star's >= 10x is against eager)
+            try:
+                out["gpu_eager_baseline"] = eager_gpu_measure(wl, B, 2, 1, dev)
+                out["gpu_eager_baseline"]["ours_over_eager"] = value / out["gpu_eager_baseline"]["value"]
+            except Exception as e:  # noqa: BLE001  (the baseline leg must never cost us the bench line)
+                out["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline and wl["kind"] in ("dual", "denoise"):
             out["cpu_baseline"] = cpu_baseline(wl, budget_s=20.0)
         emit(out)
@@ -304,12 +373,34 @@ def run_ours_dual(args, wl):
     ms_e2e = timed(step_e2e, args.steps, use_events=False)
     barrier()
     _lib.prof_read()
+    _lib.prof_read_shapes()
     _lib.prof_enable(True)
     step_resident()
     torch.cuda.synchronize()
     prof = _lib.prof_read()
+    shapes = _lib.prof_read_shapes()
     _lib.prof_enable(False)
+    # stage times of one step (CUDA events between the public calls; untimed pass)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    nav = model.model.navdp
+    ev[0].record()
+    feats = model._s2.visual(d["pixels"], grids)
+    ev[1].record()
+    lat = model._s2.prefill_latents(next_prompts(), feats, grids)
+    ev[2].record()
+    goal, rgbd = nav.goal_embed(lat), nav.rgbd_encoder(d["rgb"], d["depth"])
+    ev[3].record()
+    nav.sample(goal, rgbd, d["x0"], d["nz"])
+    ev[4].record()
+    torch.cuda.synchronize()
+    stage_ms = {"s2_vision_tower": ev[0].elapsed_time(ev[1]), "s2_plan_and_llm_prefill": ev[1].elapsed_time(ev[2]),
+                "s1_goal_and_rgbd_encoder": ev[2].elapsed_time(ev[3]), "s1_denoiser_20_steps": ev[3].elapsed_time(ev[4])}
     fl = dual_flops_per_env(wl)
+    fl_stage = {"s2_vision_tower": fl["vit"] * B, "s2_plan_and_llm_prefill": fl["llm"] * B,
+                "s1_goal_and_rgbd_encoder": fl["rgbd"] * B, "s1_denoiser_20_steps": fl["denoise"] * B}
+    stage_ms = {k: {"ms": v, "algorithmic_tflop": fl_stage[k] / 1e12, "tflops": fl_stage[k] / (v * 1e-3) / 1e12,
+                    "frac_of_sustained_peak": fl_stage[k] / (v * 1e-3) / 1e12 / peaks()["tf_sustained"]}
+                for k, v in stage_ms.items()}
     _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
             {"seq_len": wl["S"], "patches_per_env": wl["grid"][1] * wl["grid"][2], "samples_per_env": wl["Ns"],
              "horizon": wl["T"], "ddpm_steps": wl["K"], "weights": "random-init Qwen2.5-VL-7B shapes + NavDP (bf16)",
@@ -320,7 +411,7 @@ def run_ours_dual(args, wl):
              "d2h_bytes_per_step": B * 65 * 4,
              "api": "InternVLAN1ForCausalLM.dual_system_step (generate_latents + generate_traj + device action tail "
                     "n1_traj_to_actions; D2H = the action ids), pinned host inputs"},
-            fl["total"] * B)
+            fl["total"] * B, shapes=shapes, stage_ms=stage_ms)
 
 
 def _prompt_sets(wl, rank, n_sets):
@@ -764,53 +855,64 @@ def run_reference(args, wl):
     emit(out)
 
 
-def run_eager_gpu(args, wl):
-    """--impl eager: BASELINE arm, not the product -- the reference algorithm (oracle restatement, the same eager
-    PyTorch ops the reference issues) executed on the GPU in bf16 with batch = 1 per call, exactly how the reference
-    drives the model.  This is the "PyTorch-eager on the same B200" denominator of north_star's >= 10x
-    target.  Reported as policy-steps/s of one process stepping environments one after another."""
+def eager_gpu_measure(wl, batch, steps, warmup, dev=None):
+    """BASELINE, not the product: the reference algorithm as batched eager PyTorch on the GPU (oracle/eager_gpu.py: bf16,
+    cuBLAS Linears, SDPA attention), `batch` environments per call, device-timed like our arm.  -> dict for the JSON line."""
     import numpy as np
     from internnav_b200.manifest import random_navdp_state_dict, random_s2_state_dict
-    from oracle import navdp_oracle as O, qwen_oracle as Q
-    assert wl["kind"] == "dual", "--impl eager is defined for the dual_system workload"
-    dev = torch.device("cuda", 0)
+    from oracle import eager_gpu as E, navdp_oracle as O, qwen_oracle as Q
+    assert wl["kind"] == "dual", "the eager-GPU baseline is defined for the dual_system workload"
+    dev = dev or torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     cfg = dict(Q.QWEN25VL_7B)
     sd2 = random_s2_state_dict(cfg, seed=0, device=str(dev))
     sd1 = {k: v.to(dev, torch.bfloat16) for k, v in random_navdp_state_dict(seed=0).items()}
     t, h, w = wl["grid"]
-    rng = np.random.Generator(np.random.PCG64(77))
-    n_tok = t * h * w // 4
-    ids = torch.tensor([rng.integers(0, 151643, 12).tolist() + [151652] + [151655] * n_tok + [151653] +
-                        rng.integers(0, 151643, wl["S"] - 4 - n_tok - 2 - 12).tolist()])
+    B = batch
+    sets = _prompt_sets(dict(wl, B=B), 0, 4)
     g = torch.Generator(device="cpu").manual_seed(99)
-    px = torch.randn(t * h * w, 1176, generator=g).bfloat16().to(dev)
-    rgb = torch.rand(1, 2, 224, 224, 3, generator=g).bfloat16().to(dev)
-    dep = (torch.rand(1, 2, 224, 224, 1, generator=g) * 5).bfloat16().to(dev)
-    x0 = torch.randn(wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
-    nz = torch.randn(wl["K"] - 1, wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
+    px = torch.randn(B * t * h * w, 1176, generator=g).bfloat16().to(dev)
+    rgb = torch.rand(B, 2, 224, 224, 3, generator=g).bfloat16().to(dev)
+    dep = (torch.rand(B, 2, 224, 224, 1, generator=g) * 5).bfloat16().to(dev)
+    x0 = torch.randn(B * wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
+    nz = torch.randn(wl["K"] - 1, B * wl["Ns"], wl["T"], 3, generator=g).bfloat16().to(dev)
+    it = [0]
 
-    def one_env():
-        with torch.no_grad():
-            lat = Q.generate_latents(sd2, cfg, ids, px, [list(wl["grid"])])
-            traj = O.predict_pointgoal_action_async(sd1, lat, rgb, dep, x0, nz, K=wl["K"])
-        return O.traj_to_actions(traj)
+    def step():
+        it[0] += 1
+        ids = torch.tensor(sets[it[0] % len(sets)])
+        traj = E.dual_system_step(sd2, sd1, cfg, ids, px, wl["grid"], rgb, dep, x0, nz, K=wl["K"])
+        return [O.traj_to_actions(traj[b * wl["Ns"]:(b + 1) * wl["Ns"]].clone()) for b in range(B)]
 
-    for _ in range(max(args.warmup, 2)):
-        one_env()
+    for _ in range(max(warmup, 1)):
+        step()
     torch.cuda.synchronize()
-    n = max(args.steps, 3)
-    t0 = time.perf_counter()
-    for _ in range(n):
-        one_env()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / n
-    out = {"metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": 1.0 / dt, "unit": "policy-steps/s",
-           "impl": "eager_gpu", "n_gpus": 1, "steps": n, "warmup": max(args.warmup, 2), "ms_per_step": dt * 1e3,
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        tot += time.perf_counter() - t0
+    dt = tot / steps
+    del sd2, sd1
+    torch.cuda.empty_cache()
+    return {"value": B / dt, "unit": "policy-steps/s", "ms_per_step": dt * 1e3, "batch": B, "steps": steps,
+            "what": "reference algorithm as batched eager PyTorch on this GPU: bf16, cuBLAS (F.linear) + "
+                    "F.scaled_dot_product_attention, %d envs per call, wall clock incl. the numpy action tail "
+                    "(oracle/eager_gpu.py; BASELINE, none of our kernels)" % B}
+
+
+def run_eager_gpu(args, wl):
+    """--impl eager [--batch B]: the same-GPU PyTorch-eager baseline (default B = the workload's batch, 64)."""
+    B = args.batch or wl["B"]
+    r = eager_gpu_measure(wl, B, max(args.steps, 2), max(args.warmup, 1))
+    out = {"metric": "InternVLA-N1 policy-steps/sec (batch RGB-D+text->action)", "value": r["value"], "unit": "policy-steps/s",
+           "impl": "eager_gpu", "n_gpus": 1, "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": args.workload, "batch": 1,
-                      "note": "reference algorithm as eager PyTorch on the GPU (oracle restatement, bf16, explicit softmax "
-                              "attention), one environment per call like the reference; wall clock incl. the action tail"}}
+           "config": {"workload": args.workload, "batch": B, "note": r["what"]}}
     emit(out)
 
 
@@ -840,6 +942,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--workload", default="dual_system", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the same-GPU PyTorch-eager baseline leg (N = 1)")
+    ap.add_argument("--batch", type=int, default=0, help="--impl eager: environments per call (default: the workload's)")
     args = ap.parse_args()
     _claim_stdout()
     wl = WORKLOADS[args.workload]

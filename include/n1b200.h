@@ -264,6 +264,9 @@ void n1_prof_enable(int on);
 /* add kernel launches that bypassed the launchers (a replayed CUDA graph of a captured n1_* call) to the counters */
 void n1_prof_add(int64_t gemm_launches, int64_t total_launches);
 int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* total_launches);
+/* per-(M, N, K) sums of the event-timed GEMM launches that n1_prof_read has collected since the last call: mnk int32
+ * [cap, 3], count int64 [cap], ms double [cap]; returns the number of rows (< 0: error) and clears the table */
+int n1_prof_read_shapes(int32_t* mnk, int64_t* count, double* ms, int cap);
 
 /* ------------------------------------------------------------------------------------------------ kernel-level ops
  * (unit-test / profiling entry points; the model calls above are built from these) */

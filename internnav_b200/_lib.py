@@ -60,6 +60,8 @@ SYMBOLS = {
     "n1_prof_add": (None, [ctypes.c_int64, ctypes.c_int64]),
     "n1_prof_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                              ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "n1_prof_read_shapes": (c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64),
+                                    ctypes.POINTER(ctypes.c_double), c_int]),
     "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_void_p]),
     "n1_op_gemm_row384": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
@@ -133,6 +135,17 @@ def prof_read():
     c, d = ctypes.c_int64(), ctypes.c_int64()
     check(lib().n1_prof_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
     return {"gemm_ms": a.value, "gemm_flops": b.value, "gemm_launches": c.value, "total_launches": d.value}
+
+
+def prof_read_shapes(cap=256):
+    """Per-shape GEMM timing of the last profiled region (call after prof_read): list of dict(M, N, K, count, ms)."""
+    mnk = (ctypes.c_int32 * (3 * cap))()
+    cnt = (ctypes.c_int64 * cap)()
+    ms = (ctypes.c_double * cap)()
+    n = lib().n1_prof_read_shapes(mnk, cnt, ms, cap)
+    if n < 0:
+        raise N1Error(n, lib().n1_last_error().decode("utf-8", "replace"))
+    return [dict(M=mnk[3 * i], N=mnk[3 * i + 1], K=mnk[3 * i + 2], count=int(cnt[i]), ms=float(ms[i])) for i in range(n)]
 
 
 # ------------------------------------------------------------------------------------------ kernel-level ops

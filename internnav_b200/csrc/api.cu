@@ -531,6 +531,15 @@ void n1_prof_add(int64_t gemm_launches, int64_t total_launches) {
   for (int64_t i = 0; i < gemm_launches; ++i) prof_count_gemm(0.0);
 }
 
+int n1_prof_read_shapes(int32_t* mnk, int64_t* count, double* ms, int cap) {
+  int n = -1;
+  guard([&] {
+    if (!mnk || !count || !ms || cap <= 0) throw Error(N1_ERR_ARG, "n1_prof_read_shapes: bad arguments");
+    n = prof_read_shapes(mnk, reinterpret_cast<long*>(count), ms, cap);
+  });
+  return n;
+}
+
 int n1_prof_read(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* total_launches) {
   return guard([&] {
     ProfStats st = prof_read_and_reset();

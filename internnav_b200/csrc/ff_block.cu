@@ -9,16 +9,21 @@
 //   prologue (16 epilogue warps, thread = one row x 96 columns): x rows from global -> LayerNorm -> bf16 A operand in SMEM
 //       (128-byte swizzled K-major, 96 KB) AND  x + b2  in fp32 into TMEM columns 0..383 (tcgen05.st): the second GEMM
 //       then ACCUMULATES into the residual stream, so the residual add and the output bias cost no epilogue work;
-//   hidden chunks of 64 columns:  H_j = LN(x) · W1[64j:64j+64]^T  (tcgen05.mma M128 N64 into TMEM 384 + 64 (j & 1))
-//       -> 8 of the 16 epilogue warps (group j & 1): tcgen05.ld, + b1, GELU (packed f32x2 polynomial, no MUFU), bf16,
-//          swizzled SMEM chunk  ->  x_tmem += H_j · W2[:, 64j:64j+64]^T   (2 x M128 N192 per k-step);
+//   hidden chunks of 128 columns:  H_j = LN(x) · W1[128j:128j+128]^T  (tcgen05.mma M128 N128 into TMEM 384..511)
+//       -> all 16 epilogue warps: tcgen05.ld (32 columns each), + b1, GELU (packed f32x2 polynomial, no MUFU), bf16,
+//          swizzled SMEM chunk  ->  x_tmem += H_j · W2[:, 128j:128j+128]^T   (2 x M128 N192 per k-step);
+//       one TMEM and one SMEM chunk buffer: GEMM1(j+1) runs while chunk j is in the GELU epilogue, GEMM2(j) while chunk
+//       j+1 is.  (The first version used 64-column chunks, double buffered: its 768 small MMAs per tile made the single
+//       issuing thread the limiter -- tensor pipe 25 % active, no barrier ever waited on, profiles/r2_ncu_ff_block_v0_*.)
 //   W1 / W2 slices stream through a 4 x 24 KB TMA ring; CM = 2: the two CTAs of a cluster fetch half a slice each and
-//       multicast it (halves the L2 -> SMEM weight traffic, the limiter of this short-K shape);
+//       multicast it;
 //   final epilogue: TMEM 0..383 -> bf16 -> SMEM staging -> TMA store to x (in place).
 //
 // Differences from the first fused MLP (fused_mlp.cu, kept for reference): LayerNorm inside, residual in TMEM, 16
 // epilogue warps instead of 8 (the GELU epilogue was the limiter: 2 warps per scheduler could not hide FMA latency), and
 // a MUFU-free GELU in packed fp32.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "n1_ops.h"
@@ -27,16 +32,15 @@
 namespace n1 {
 namespace {
 
-constexpr int D = 384, F = 1536, BM = 128, HC = 64;
-constexpr int NCH = F / HC;                          // 24 hidden chunks
-constexpr int kSlots = 4, kSlotBytes = 24576;
-constexpr int kLag = 2;                              // GEMM2(j) is issued after GEMM1(j + kLag)
+constexpr int D = 384, F = 1536, BM = 128, HC = 128;
+constexpr int NCH = F / HC;                          // 12 hidden chunks
+constexpr int kSlots = 4, kSlotBytes = 24576;        // one W1 k-block [128 x 64] (16 KB) or one W2 half [192 x 64] (24 KB)
 constexpr int kABytes = BM * D * 2;                  // 98304: 6 k-blocks of [128 x 64]
-constexpr int kHBytes = BM * HC * 2;                 // 16384 per buffer
+constexpr int kHBytes = BM * HC * 2;                 // 32768: the GELU(H) chunk, 2 k-blocks of [128 x 64]
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;        // 576
 constexpr int kStatBytes = 128 * 2 * 4;              // LayerNorm statistics of the tile: [128 rows][mean, rstd]
-constexpr int kSmem = kABytes + 2 * kHBytes + kSlots * kSlotBytes + kStatBytes + 512 + 1024;
+constexpr int kSmem = kABytes + kHBytes + kSlots * kSlotBytes + kStatBytes + 512 + 1024;
 
 struct FfArgs {
   int M;
@@ -84,7 +88,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // barrier among the 16 epilogue warps only (named barrier 1; warps 0 and 1 never join it)
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-template <int CM>
+// UI: the MMA warp runs its loop with all lanes and an elected lane issues (operands stay in uniform registers)
+template <int CM, bool UI>
+// 18 warps = 5 on one scheduler: 16384 / (5 * 32) = 102 -> ptxas settles on 96 registers per thread
 __global__ void __launch_bounds__(kThreads, 1)
 ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 const __grid_constant__ CUtensorMap tmOut, const FfArgs args) {
@@ -93,16 +99,16 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sH = smem + kABytes;
-  uint8_t* sW = sH + 2 * kHBytes;
+  uint8_t* sW = sH + kHBytes;
   float* sStat = reinterpret_cast<float*>(sW + kSlots * kSlotBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kSlots * kSlotBytes + kStatBytes);
   uint64_t* w_full = bars;                 // [4]
   uint64_t* w_empty = bars + 4;            // [4]
   uint64_t* a_full = bars + 8;             // LN(x) operand written and x + b2 seeded in TMEM (16 warp arrivals)
-  uint64_t* hacc_full = bars + 10;         // [2] GEMM1(j) complete -> TMEM H readable
-  uint64_t* hacc_empty = bars + 12;        // [2] epilogue group finished reading TMEM H (8 warp arrivals)
-  uint64_t* hs_full = bars + 14;           // [2] SMEM H written (8 warp arrivals)
-  uint64_t* hs_empty = bars + 16;          // [2] GEMM2 finished reading SMEM H
+  uint64_t* hacc_full = bars + 10;         // GEMM1(j) complete -> TMEM H readable
+  uint64_t* hacc_empty = bars + 12;        // epilogue finished reading TMEM H (16 warp arrivals)
+  uint64_t* hs_full = bars + 14;           // SMEM H written (16 warp arrivals)
+  uint64_t* hs_empty = bars + 16;          // GEMM2 finished reading SMEM H
   uint64_t* y_full = bars + 18;            // all MMAs of the tile complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
@@ -115,10 +121,8 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     tma_prefetch_desc(&tmW1), tma_prefetch_desc(&tmW2), tma_prefetch_desc(&tmOut);
     for (int s = 0; s < kSlots; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], CM);
     mbar_init(a_full, kEpiWarps);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&hacc_full[b], 1), mbar_init(&hacc_empty[b], 8);
-      mbar_init(&hs_full[b], 8), mbar_init(&hs_empty[b], 1);
-    }
+    mbar_init(hacc_full, 1), mbar_init(hacc_empty, kEpiWarps);
+    mbar_init(hs_full, kEpiWarps), mbar_init(hs_empty, 1);
     mbar_init(y_full, 1);
     fence_mbar_init();
   }
@@ -137,96 +141,107 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       int slot = 0;
       uint32_t wphase = 0;
       auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
+      auto load_w1 = [&](int j) {  // W1 rows [128j, 128j+128): six k-blocks, one slot each
+        for (int kb = 0; kb < D / 64; ++kb) {
+          mbar_wait(&w_empty[slot], wphase ^ 1);
+          mbar_arrive_expect_tx(&w_full[slot], 16384);
+          uint8_t* dst = sW + slot * kSlotBytes;
+          if (CM == 1) {
+            tma_load_2d(dst, &tmW1, &w_full[slot], kb * 64, j * HC);
+          } else {  // each CTA fetches 64 of the 128 rows and multicasts them
+            tma_load_2d_mc(dst + rank * 8192, &tmW1, &w_full[slot], kb * 64, j * HC + rank * 64, kMask);
+          }
+          next();
+        }
+      };
+      auto load_w2 = [&](int j) {  // W2[:, 128j : 128j+128): per k-block two N-halves of 192 rows, one slot each
+        for (int kb = 0; kb < HC / 64; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_empty[slot], wphase ^ 1);
+            mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
+            uint8_t* dst = sW + slot * kSlotBytes;
+            if (CM == 1) {
+              tma_load_2d(dst, &tmW2, &w_full[slot], j * HC + kb * 64, nh * 192);
+            } else {
+              tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], j * HC + kb * 64, nh * 192 + rank * 96, kMask);
+            }
+            next();
+          }
+      };
       for (int t = cluster_id; t < super_m; t += num_clusters) {
-        for (int j = 0; j < NCH + kLag; ++j) {
-          if (j < NCH) {  // W1 rows [64j, 64j+64): two half-slices of 3 k-blocks
-            for (int hf = 0; hf < 2; ++hf) {
-              mbar_wait(&w_empty[slot], wphase ^ 1);
-              mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
-              uint8_t* dst = sW + slot * kSlotBytes;
-              for (int kb = 0; kb < 3; ++kb) {
-                if (CM == 1) {
-                  tma_load_2d(dst + kb * 8192, &tmW1, &w_full[slot], (hf * 3 + kb) * 64, j * HC);
-                } else {  // each CTA fetches 32 of the 64 rows and multicasts them
-                  tma_load_2d_mc(dst + kb * 8192 + rank * 4096, &tmW1, &w_full[slot], (hf * 3 + kb) * 64,
-                                 j * HC + rank * 32, kMask);
-                }
-              }
-              next();
-            }
-          }
-          if (j >= kLag) {  // W2[:, 64(j-kLag) : +64): two N-halves of 192 rows
-            for (int nh = 0; nh < 2; ++nh) {
-              mbar_wait(&w_empty[slot], wphase ^ 1);
-              mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
-              uint8_t* dst = sW + slot * kSlotBytes;
-              if (CM == 1) {
-                tma_load_2d(dst, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192);
-              } else {
-                tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], (j - kLag) * HC, nh * 192 + rank * 96, kMask);
-              }
-              next();
-            }
-          }
+        load_w1(0);
+        for (int j = 0; j < NCH; ++j) {  // the order the MMA warp consumes: GEMM1(j + 1), then GEMM2(j)
+          if (j + 1 < NCH) load_w1(j + 1);
+          load_w2(j);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (UI || lane == 0) {
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (UI) umma_f16_elect(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) { if (UI) umma_commit_elect(bar); else umma_commit(bar); };
       constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);
       constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 192);
       int slot = 0;
-      uint32_t wphase = 0, tphase = 0;
-      uint32_t hacc_ph[2] = {0, 0}, hs_ph[2] = {0, 0};
+      uint32_t wphase = 0, tphase = 0, hacc_ph = 0, hs_ph = 0;
       auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
-      auto release = [&](uint64_t* bar) { if (CM == 1) umma_commit(bar); else umma_commit_mc(bar, kMask); };
+      auto release = [&](uint64_t* bar) {
+        if (CM == 1) commit(bar);
+        else if (UI) umma_commit_mc_elect(bar, kMask);
+        else umma_commit_mc(bar, kMask);
+      };
+      auto gemm1 = [&]() {  // TMEM[384..511] = LN(x) · W1 chunk^T, K = 384: 6 k-blocks x 4 k-steps of M128 N128 K16
+        for (int kb = 0; kb < D / 64; ++kb) {
+          mbar_wait(&w_full[slot], wphase);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + kb * 16384));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma(tmem + 384, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+          release(&w_empty[slot]);
+          next();
+        }
+        commit(hacc_full);
+      };
+      auto gemm2 = [&]() {  // x_tmem[0..383] += GELU(H chunk) · W2 chunk^T, K = 128: 2 k-blocks x 2 N-halves x 4 k-steps
+        for (int kb = 0; kb < HC / 64; ++kb) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sH + kb * 16384));
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_full[slot], wphase);
+            tc_fence_after();
+            const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(tmem + nh * 192, ad + 2 * k, bd + 2 * k, idesc2, 1u);
+            release(&w_empty[slot]);
+            next();
+          }
+        }
+        commit(hs_empty);
+      };
       for (int t = cluster_id; t < super_m; t += num_clusters) {
         mbar_wait(a_full, tphase);   // LN(x) in SMEM, x + b2 in TMEM columns 0..383
         tc_fence_after();
-        for (int j = 0; j < NCH + kLag; ++j) {
-          if (j < NCH) {
-            const int b = j & 1;
-            mbar_wait(&hacc_empty[b], hacc_ph[b] ^ 1);  // epilogue done with the previous use of TMEM H[b]
+        gemm1();                     // chunk 0 (TMEM H is free: the previous tile's last chunk was read before its GEMM2)
+        for (int j = 0; j < NCH; ++j) {
+          if (j + 1 < NCH) {
+            mbar_wait(hacc_empty, hacc_ph);  // the epilogue holds chunk j in registers: TMEM H may be overwritten
+            hacc_ph ^= 1;
             tc_fence_after();
-            for (int hf = 0; hf < 2; ++hf) {
-              mbar_wait(&w_full[slot], wphase);
-              tc_fence_after();
-#pragma unroll
-              for (int kb = 0; kb < 3; ++kb) {
-                const uint64_t ad = umma_desc_sw128(smem_u32(sA + (hf * 3 + kb) * 16384));
-                const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes + kb * 8192));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(tmem + 384 + b * HC, ad + 2 * k, bd + 2 * k, idesc1, (hf | kb | k) != 0 ? 1u : 0u);
-              }
-              release(&w_empty[slot]);
-              next();
-            }
-            umma_commit(&hacc_full[b]);
-            hacc_ph[b] ^= 1;
+            gemm1();
           }
-          if (j >= kLag) {  // GEMM2 trails GEMM1 by kLag chunks so the tensor pipe has work while GELU(H) is produced
-            const int jj = j - kLag, b = jj & 1;
-            mbar_wait(&hs_full[b], hs_ph[b]);  // GELU(H_jj) is in shared memory
-            hs_ph[b] ^= 1;
-            tc_fence_after();
-            const uint64_t ad = umma_desc_sw128(smem_u32(sH + b * kHBytes));
-            for (int nh = 0; nh < 2; ++nh) {
-              mbar_wait(&w_full[slot], wphase);
-              tc_fence_after();
-              const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(tmem + nh * 192, ad + 2 * k, bd + 2 * k, idesc2, 1u);  // accumulates onto x + b2
-              release(&w_empty[slot]);
-              next();
-            }
-            umma_commit(&hs_empty[b]);
-          }
+          mbar_wait(hs_full, hs_ph);         // GELU(H_j) is in shared memory
+          hs_ph ^= 1;
+          tc_fence_after();
+          gemm2();
         }
-        umma_commit(y_full);
+        // the last chunk's hacc_empty arrival is consumed here so that the phases stay aligned across tiles
+        mbar_wait(hacc_empty, hacc_ph);
+        hacc_ph ^= 1;
+        commit(y_full);
         tphase ^= 1;
       }
     }
@@ -235,8 +250,7 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     // ------------------------------------------------------------------ 16 epilogue warps
     const int ew = warp - 2;                 // 0..15
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-    const int sub = ew >> 2;                 // 0..3: which of the 4 warps of this quarter
-    const int grp = sub & 1, colhalf = sub >> 1;   // GELU: hidden-chunk group (= H buffer) and 32-column half
+    const int sub = ew >> 2;                 // 0..3: which of the 4 warps of this quarter (= its 32-column slice of a chunk)
     const int r_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     uint32_t hacc_phase = 0, hs_phase = 0, tphase = 0;
@@ -317,19 +331,18 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
 
-      // ---- hidden chunks: group `grp` (8 warps) owns the chunks j = grp, grp + 2, ...; this warp its 32-column half
-      for (int j = grp; j < NCH; j += 2) {
-        const int b = grp;
-        mbar_wait(&hacc_full[b], hacc_phase);
+      // ---- hidden chunks: every warp takes its 32 columns of every chunk
+      for (int j = 0; j < NCH; ++j) {
+        mbar_wait(hacc_full, hacc_phase);
         hacc_phase ^= 1;
         tc_fence_after();
         uint32_t r0[32];
-        tmem_ld32(tmem + lane_base + 384 + b * HC + colhalf * 32, r0);
+        tmem_ld32(tmem + lane_base + 384 + sub * 32, r0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hacc_empty[b]);
-        const float* bias = args.b1 + j * HC + colhalf * 32;
+        if (lane == 0) mbar_arrive(hacc_empty);
+        const float* bias = args.b1 + j * HC + sub * 32;
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
@@ -338,18 +351,19 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
           const float2 g1 = gelu2(make_float2(__uint_as_float(r0[c + 2]) + bb.z, __uint_as_float(r0[c + 3]) + bb.w));
           pk[c / 2] = pack_bf16(g0.x, g0.y), pk[c / 2 + 1] = pack_bf16(g1.x, g1.y);
         }
-        mbar_wait(&hs_empty[b], hs_phase ^ 1);  // GEMM2(j - 2) has finished reading this buffer
+        mbar_wait(hs_empty, hs_phase ^ 1);  // GEMM2(j - 1) has finished reading the chunk buffer
         hs_phase ^= 1;
-        uint8_t* rowp = sH + b * kHBytes + (r_in_tile >> 3) * 1024 + (r_in_tile & 7) * 128;
+        // chunk column c lives in k-block c / 64, 16-byte chunk (c % 64) / 8 at position chunk ^ (row % 8)
+        uint8_t* rowp = sH + (sub >> 1) * 16384 + (r_in_tile >> 3) * 1024 + (r_in_tile & 7) * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int ch = colhalf * 4 + c;
+          const int ch = (sub & 1) * 4 + c;
           *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_in_tile & 7)) << 4)) =
               make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hs_full[b]);
+        if (lane == 0) mbar_arrive(hs_full);
       }
       // ---- final epilogue: TMEM columns 0..383 already hold x + b2 + FF(LN(x)); 3 chunks of 32 columns per warp
       mbar_wait(y_full, tphase);
@@ -393,12 +407,21 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   }
 }
 
-template <int CM>
+int ff_uniform_issue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("N1_FF_UI");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int CM, bool UI>
 void launch_ff(const bf16* w1, const bf16* w2, const FfArgs& a, bf16* out, int ldo, cudaStream_t stream) {
   static std::once_flag once;
   static int max_clusters = 0;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(ff_block_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(ff_block_kernel<CM, UI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     max_clusters = device_sm_count() / CM;
     if (CM > 1) {
       cudaLaunchConfig_t cfg = {};
@@ -408,7 +431,7 @@ void launch_ff(const bf16* w1, const bf16* w2, const FfArgs& a, bf16* out, int l
       at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
       cfg.attrs = &at, cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, ff_block_kernel<CM>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, ff_block_kernel<CM, UI>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
     }
   });
   CUtensorMap tmW1 = tma_map_2d(w1, F, D, D, HC / CM, 64, true);
@@ -422,7 +445,9 @@ void launch_ff(const bf16* w1, const bf16* w2, const FfArgs& a, bf16* out, int l
   at.id = cudaLaunchAttributeClusterDimension;
   at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
   cfg.attrs = &at, cfg.numAttrs = 1;
-  N1_CUDA(cudaLaunchKernelEx(&cfg, ff_block_kernel<CM>, tmW1, tmW2, tmOut, a));
+  const int ticket = prof_begin(4.0 * a.M * (double)D * F, a.M, -F, D, stream);  // N = -1536 marks the fused FF block
+  N1_CUDA(cudaLaunchKernelEx(&cfg, ff_block_kernel<CM, UI>, tmW1, tmW2, tmOut, a));
+  prof_end(ticket, stream);
   prof_count_gemm(4.0 * a.M * (double)D * F);
   N1_CUDA(cudaGetLastError());
 }
@@ -439,10 +464,12 @@ void ff_block_384(const bf16* x, int ldx, const float* ln_w, const float* ln_b, 
   FfArgs a;
   a.M = M, a.tiles_m = (M + BM - 1) / BM;
   a.x = x, a.ldx = ldx, a.ln_w = ln_w, a.ln_b = ln_b, a.eps = eps, a.b1 = b1, a.b2 = b2;
-  if (cluster >= 2 && a.tiles_m >= 2)
-    launch_ff<2>(w1, w2, a, out, ldo, stream);
-  else
-    launch_ff<1>(w1, w2, a, out, ldo, stream);
+  const bool ui = ff_uniform_issue() != 0;
+  if (cluster >= 2 && a.tiles_m >= 2) {
+    if (ui) launch_ff<2, true>(w1, w2, a, out, ldo, stream); else launch_ff<2, false>(w1, w2, a, out, ldo, stream);
+  } else {
+    if (ui) launch_ff<1, true>(w1, w2, a, out, ldo, stream); else launch_ff<1, false>(w1, w2, a, out, ldo, stream);
+  }
 }
 
 }  // namespace n1

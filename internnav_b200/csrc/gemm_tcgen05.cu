@@ -494,8 +494,15 @@ std::mutex g_prof_mu;
 struct EvPair {
   cudaEvent_t a, b;
   double flops;
+  int M, N, K;
 };
 std::vector<EvPair> g_events;
+struct ShapeAcc {
+  int M, N, K;
+  long count;
+  double ms;
+};
+std::vector<ShapeAcc> g_shapes;  // per-(M, N, K) sums of the event-timed launches since the last prof_read_shapes()
 
 }  // namespace
 
@@ -510,6 +517,23 @@ void prof_count_gemm(double flops) {
 }
 
 void prof_enable(bool on) { g_prof_on = on; }
+// Event bracket for GEMM-class kernels launched outside gemm_bf16 (the fused decoder blocks): returns a ticket (< 0: off)
+int prof_begin(double flops, int M, int N, int K, cudaStream_t s) {
+  if (!g_prof_on.load()) return -1;
+  EvPair ev{};
+  cudaEventCreate(&ev.a);
+  cudaEventCreate(&ev.b);
+  ev.flops = flops, ev.M = M, ev.N = N, ev.K = K;
+  cudaEventRecord(ev.a, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_events.push_back(ev);
+  return (int)g_events.size() - 1;
+}
+void prof_end(int ticket, cudaStream_t s) {
+  if (ticket < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (ticket < (int)g_events.size()) cudaEventRecord(g_events[ticket].b, s);
+}
 void prof_count_launch(int n) { g_total_launches += n; }
 ProfStats prof_read_and_reset() {
   ProfStats st;
@@ -517,7 +541,16 @@ ProfStats prof_read_and_reset() {
   for (EvPair& e : g_events) {
     cudaEventSynchronize(e.b);
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) st.gemm_ms += ms, st.gemm_flops += e.flops;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      st.gemm_ms += ms, st.gemm_flops += e.flops;
+      bool hit = false;
+      for (ShapeAcc& sa : g_shapes)
+        if (sa.M == e.M && sa.N == e.N && sa.K == e.K) {
+          sa.count++, sa.ms += ms, hit = true;
+          break;
+        }
+      if (!hit) g_shapes.push_back({e.M, e.N, e.K, 1, (double)ms});
+    }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
@@ -525,6 +558,19 @@ ProfStats prof_read_and_reset() {
   st.gemm_launches = g_gemm_launches.exchange(0);
   st.total_launches = g_total_launches.exchange(0);
   return st;
+}
+
+int prof_read_shapes(int* mnk, long* count, double* ms, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (const ShapeAcc& sa : g_shapes) {
+    if (n >= cap) break;
+    mnk[3 * n] = sa.M, mnk[3 * n + 1] = sa.N, mnk[3 * n + 2] = sa.K;
+    count[n] = sa.count, ms[n] = sa.ms;
+    ++n;
+  }
+  g_shapes.clear();
+  return n;
 }
 
 int device_sm_count() {
@@ -571,6 +617,7 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
     cudaEventCreate(&ev.a);
     cudaEventCreate(&ev.b);
     ev.flops = 2.0 * M * (double)N * K;
+    ev.M = M, ev.N = N, ev.K = K;
     cudaEventRecord(ev.a, stream);
   }
   g_gemm_launches++;

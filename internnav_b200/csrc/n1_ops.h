@@ -83,7 +83,11 @@ struct ProfStats {
 };
 void prof_enable(bool on);
 void prof_count_launch(int n = 1);
+int prof_begin(double flops, int M, int N, int K, cudaStream_t s);  // event bracket of a GEMM-class kernel (prof on)
+void prof_end(int ticket, cudaStream_t s);
 ProfStats prof_read_and_reset();
+// per-shape sums of the event-timed GEMM launches accumulated by prof_read_and_reset(); clears the table; returns rows
+int prof_read_shapes(int* mnk, long* count, double* ms, int cap);
 
 // ------------------------------------------------------------------------------------------- norms
 // y = LayerNorm(x) * w + b  (rms=0)   or   y = x / rms(x) * w  (rms=1);  one warp per row; D % 8 == 0.

@@ -163,6 +163,44 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// Warp-uniform issue: called by ALL lanes of a converged warp, one elected lane issues.  With the issue loop executed by
+// the whole warp its operands (descriptors, TMEM addresses) stay in uniform registers; a loop under `if (lane == 0)` makes
+// the compiler move every descriptor through R2UR + ELECT + R2UR.BROADCAST before each tcgen05.mma (~14 instructions per
+// MMA: profiles/r2_ncu_ff_block_v0_summary.txt), which left the single issuing thread -- not the tensor pipe -- as the
+// limiter for MMAs narrower than N = 256.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // Same, arriving on the barrier at this offset in every CTA of `cta_mask` (cluster multicast).
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(

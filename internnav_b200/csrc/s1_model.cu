@@ -48,12 +48,14 @@ int row384_mode() {
 // N1_FUSED_MLP: 0 (default) = two GEMMs, 1 = fused kernel, 2 = fused kernel with 2-CTA weight multicast.
 // The fused kernel (fused_mlp.cu) is EXPERIMENTAL and off: it is correct when it completes, but it is slower than the
 // two-GEMM path (GELU issue-bound, ~400 vs ~320 us at 65536 rows) and a rare hang was seen under pytest on B200.
-// N1_FF_BLOCK: 0 = off (LayerNorm + FF1 + FF2 as three kernels), 1 / 2 = the FF-block kernel (cluster size)
+// N1_FF_BLOCK: 0 = LayerNorm + FF1 + FF2 as three kernels, 1 / 2 = the FF-block kernel (cluster size).  Default 1:
+// validated on B200 (tests/test_ops_gpu.py::test_ff_block, profiles/r2_ff_block_tests_v0.log) and 6 % faster per
+// dual-system step than the three-kernel form (profiles/r2_bench_dual_system_ffblock_v0.json).
 int ff_block_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("N1_FF_BLOCK");
-    mode = e ? atoi(e) : 0;
+    mode = e ? atoi(e) : 1;
   }
   return mode;
 }
