@@ -304,6 +304,15 @@ int n1_op_attention(const void* q, const void* k, const void* v, void* o, int ld
                     int heads_kv, int head_dim, int batch, int seq_q, int seq_k, const int32_t* cu_q,
                     const int32_t* cu_k, int max_seq_q, int kv_div, int causal, float scale, void* stream);
 
+/* Var-len self-attention (cu_seqlens int32 [batch + 1] on the device, q / k / v packed with row strides) with the row count
+ * of the buffers given: head_dim 128 and <= 320 tokens per sequence run on the tcgen05 kernel (Q K^T and P V on
+ * tcgen05.mma, scores in tensor memory, TMA-loaded tiles) -- the decoder prefill attention of generate_latents
+ * (internvla_n1.py L206 / L338; flash_attention_2 in the reference, internvla_n1_policy.py L36).  *used_tcgen05 reports
+ * which kernel ran (N1_ATTN_TC=0 forces the mma.sync kernel). */
+int n1_op_attention_ex(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo, int heads_q,
+                       int heads_kv, int head_dim, int batch, const int32_t* cu_seqlens, int max_seq, int64_t total_rows,
+                       int causal, float scale, int* used_tcgen05, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

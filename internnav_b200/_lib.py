@@ -75,6 +75,8 @@ SYMBOLS = {
                                   c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
                                 c_void_p]),
+    "n1_op_attention_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_int, ctypes.c_int64, c_int, c_float, ctypes.POINTER(c_int), c_void_p]),
     "n1_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
 }
@@ -202,6 +204,21 @@ def attention(q, k, v, heads_q, heads_kv, head_dim, batch, seq_q, seq_k, cu_q=No
                                 seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div, 1 if causal else 0,
                                 float(scale), stream_ptr()))
     return o
+
+
+def attention_varlen(q, k, v, heads_q, heads_kv, head_dim, cu_seqlens, max_seq, causal=True, scale=None):
+    """Var-len self-attention over packed rows (q / k / v: views with unit inner stride, `cu_seqlens` int32 [batch + 1]).
+    -> (o [rows, heads_q * hd], used_tcgen05: whether the tcgen05 kernel ran)."""
+    assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    o = torch.empty(q.shape[0], heads_q * head_dim, device=q.device, dtype=torch.bfloat16)
+    if scale is None:
+        scale = head_dim ** -0.5
+    used = c_int(0)
+    check(lib().n1_op_attention_ex(c_void_p(q.data_ptr()), c_void_p(k.data_ptr()), c_void_p(v.data_ptr()), ptr(o),
+                                   q.stride(0), k.stride(0), v.stride(0), o.stride(0), heads_q, heads_kv, head_dim,
+                                   cu_seqlens.numel() - 1, ptr(cu_seqlens), int(max_seq), q.shape[0], 1 if causal else 0,
+                                   float(scale), ctypes.byref(used), stream_ptr()))
+    return o, bool(used.value)
 
 
 def fused_mlp(x, w1, b1, w2, b2, residual=None, out=None, cluster=2):

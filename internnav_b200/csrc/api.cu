@@ -614,4 +614,21 @@ int n1_op_attention(const void* q, const void* k, const void* v, void* o, int ld
   });
 }
 
+/* n1_op_attention with the row count of the packed buffers: lets var-len self-attention with head_dim 128 and <= 320
+ * tokens per sequence take the tcgen05 kernel (attention_tc.cu), which addresses q / k / v through TMA tensor maps */
+int n1_op_attention_ex(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo, int heads_q,
+                       int heads_kv, int head_dim, int batch, const int32_t* cu_seqlens, int max_seq, int64_t total_rows,
+                       int causal, float scale, int* used_tcgen05, void* stream) {
+  return guard([&] {
+    AttnParams p = {};
+    p.q = B16(q), p.k = B16(k), p.v = B16(v), p.o = B16(o);
+    p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.ldo = ldo;
+    p.heads_q = heads_q, p.heads_kv = heads_kv, p.hd = head_dim, p.batch = batch;
+    p.cu_q = p.cu_k = cu_seqlens, p.max_seq_q = max_seq, p.total_rows = total_rows;
+    p.kv_div = 1, p.causal = causal, p.scale = scale;
+    if (used_tcgen05) *used_tcgen05 = (head_dim == 128 && attention_tc_supported(p)) ? 1 : 0;
+    attention(p, S(stream));
+  });
+}
+
 }  // extern "C"

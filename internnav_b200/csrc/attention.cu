@@ -13,6 +13,8 @@
 // 64-key tiles through a 2-stage cp.async ring; S = QK^T and O += PV on mma.sync.m16n8k16 (bf16, fp32 accumulate)
 // with ldmatrix operand fetch; online softmax in registers with quad shuffles.
 // TODO(round 2): tcgen05 path for the hd-128 prefill (attention is < 5 % of the path's FLOPs).
+#include <stdlib.h>
+
 #include "n1_ops.h"
 #include "n1_ptx.cuh"
 
@@ -417,6 +419,17 @@ void attention(const AttnParams& p, cudaStream_t stream) {
     else if (nkp == 3) launch_attn_small<3>(p, stream);
     else launch_attn_small<4>(p, stream);
     return;
+  }
+  if (p.hd == 128 && attention_tc_supported(p)) {
+    static int tc = -1;  // N1_ATTN_TC=0 keeps the mma.sync kernel
+    if (tc < 0) {
+      const char* e = getenv("N1_ATTN_TC");
+      tc = e ? atoi(e) : 1;
+    }
+    if (tc) {
+      attention_tc128(p, stream);
+      return;
+    }
   }
   switch (p.hd) {
     case 48: launch_attn<48>(p, stream); break;

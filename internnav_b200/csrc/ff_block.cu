@@ -15,8 +15,11 @@
 //       one TMEM and one SMEM chunk buffer: GEMM1(j+1) runs while chunk j is in the GELU epilogue, GEMM2(j) while chunk
 //       j+1 is.  (The first version used 64-column chunks, double buffered: its 768 small MMAs per tile made the single
 //       issuing thread the limiter -- tensor pipe 25 % active, no barrier ever waited on, profiles/r2_ncu_ff_block_v0_*.)
-//   W1 / W2 slices stream through a 4 x 24 KB TMA ring; CM = 2: the two CTAs of a cluster fetch half a slice each and
-//       multicast it;
+//   TWO MMA-issuing warps (GEMM1 and GEMM2 each have their own issuer, TMA producer and weight ring): one thread can
+//       issue a tcgen05.mma only every ~100-150 cycles (descriptor moves into uniform registers), which is longer than an
+//       N = 128 / N = 192 MMA occupies the tensor pipe (64 / 96 cycles) -- with one issuer (v1) the pipe was 30 % busy;
+//   W1 streams through a 3 x 16 KB ring, W2 through a 2 x 24 KB ring; CM = 2: the two CTAs of a cluster fetch half a slice
+//       each and multicast it;
 //   final epilogue: TMEM 0..383 -> bf16 -> SMEM staging -> TMA store to x (in place).
 //
 // Differences from the first fused MLP (fused_mlp.cu, kept for reference): LayerNorm inside, residual in TMEM, 16
@@ -34,13 +37,14 @@ namespace {
 
 constexpr int D = 384, F = 1536, BM = 128, HC = 128;
 constexpr int NCH = F / HC;                          // 12 hidden chunks
-constexpr int kSlots = 4, kSlotBytes = 24576;        // one W1 k-block [128 x 64] (16 KB) or one W2 half [192 x 64] (24 KB)
+constexpr int kS1 = 3, kS1Bytes = 16384;             // W1 ring: one k-block [128 x 64] of a hidden chunk per slot
+constexpr int kS2 = 2, kS2Bytes = 24576;             // W2 ring: one N-half [192 x 64] of a k-block per slot
 constexpr int kABytes = BM * D * 2;                  // 98304: 6 k-blocks of [128 x 64]
 constexpr int kHBytes = BM * HC * 2;                 // 32768: the GELU(H) chunk, 2 k-blocks of [128 x 64]
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = 64 + 32 * kEpiWarps;        // 576
+constexpr int kThreads = 128 + 32 * kEpiWarps;       // 640: 2 TMA producers, 2 MMA issuers, 16 epilogue warps
 constexpr int kStatBytes = 128 * 2 * 4;              // LayerNorm statistics of the tile: [128 rows][mean, rstd]
-constexpr int kSmem = kABytes + kHBytes + kSlots * kSlotBytes + kStatBytes + 512 + 1024;
+constexpr int kSmem = kABytes + kHBytes + kS1 * kS1Bytes + kS2 * kS2Bytes + kStatBytes + 512 + 1024;
 
 struct FfArgs {
   int M;
@@ -54,43 +58,30 @@ struct FfArgs {
   const float* b2;
 };
 
-// erf(u / sqrt 2) ~= u P(u^2) on |u| <= 4 (least-squares fit weighted for the GELU product, |gelu error| <= 2.0e-4,
-// i.e. a fraction of a bf16 ulp of the result; the clamp makes it exactly +-1 beyond).  Two values per instruction.
+// erf(u / sqrt 2) ~= u P(u^2) on |u| <= 4: least-squares fit weighted for the GELU product, scaled by (1 - 1e-4) so that
+// |u P(u^2)| < 1 everywhere and no clamp of the result is needed.  |gelu error| <= 3e-4 for |x| <= 4 and <= 4e-5 |x|
+// beyond (a fraction of a bf16 ulp of the result).  Packed fp32: two values per instruction, no MUFU.
 __device__ __forceinline__ float2 gelu2(float2 x) {
   const float2 u = make_float2(fminf(fmaxf(x.x, -4.0f), 4.0f), fminf(fmaxf(x.y, -4.0f), 4.0f));
   const float2 s = __fmul2_rn(u, u);
-  float2 p = __ffma2_rn(make_float2(4.4781046e-08f, 4.4781046e-08f), s, make_float2(-3.156104e-06f, -3.156104e-06f));
-  p = __ffma2_rn(p, s, make_float2(9.50805e-05f, 9.50805e-05f));
-  p = __ffma2_rn(p, s, make_float2(-0.0016200024f, -0.0016200024f));
-  p = __ffma2_rn(p, s, make_float2(0.017507503f, 0.017507503f));
-  p = __ffma2_rn(p, s, make_float2(-0.12907527f, -0.12907527f));
-  p = __ffma2_rn(p, s, make_float2(0.7957365f, 0.7957365f));
-  float2 e = __fmul2_rn(u, p);
-  e = make_float2(fminf(fmaxf(e.x, -1.0f), 1.0f), fminf(fmaxf(e.y, -1.0f), 1.0f));
+  float2 p = __ffma2_rn(make_float2(4.477657000734325e-08f, 4.477657000734325e-08f), s,
+                        make_float2(-3.1557883630739525e-06f, -3.1557883630739525e-06f));
+  p = __ffma2_rn(p, s, make_float2(9.507098729955032e-05f, 9.507098729955032e-05f));
+  p = __ffma2_rn(p, s, make_float2(-0.001619840506464243f, -0.001619840506464243f));
+  p = __ffma2_rn(p, s, make_float2(0.01750575192272663f, 0.01750575192272663f));
+  p = __ffma2_rn(p, s, make_float2(-0.12906235456466675f, -0.12906235456466675f));
+  p = __ffma2_rn(p, s, make_float2(0.7956569194793701f, 0.7956569194793701f));
+  const float2 e = __fmul2_rn(u, p);
   const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(h, e, h);
 }
 
-// registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// barrier among the 16 epilogue warps only (named barrier 1; warps 0 and 1 never join it)
+// barrier among the 16 epilogue warps only (named barrier 1; the producer / MMA warps never join it)
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // UI: the MMA warp runs its loop with all lanes and an elected lane issues (operands stay in uniform registers)
 template <int CM, bool UI>
-// 18 warps = 5 on one scheduler: 16384 / (5 * 32) = 102 -> ptxas settles on 96 registers per thread
+// 20 warps = 5 per scheduler: 16384 / (5 * 32) = 102 -> ptxas settles on 96 registers per thread
 __global__ void __launch_bounds__(kThreads, 1)
 ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 const __grid_constant__ CUtensorMap tmOut, const FfArgs args) {
@@ -99,18 +90,21 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sH = smem + kABytes;
-  uint8_t* sW = sH + kHBytes;
-  float* sStat = reinterpret_cast<float*>(sW + kSlots * kSlotBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kSlots * kSlotBytes + kStatBytes);
-  uint64_t* w_full = bars;                 // [4]
-  uint64_t* w_empty = bars + 4;            // [4]
-  uint64_t* a_full = bars + 8;             // LN(x) operand written and x + b2 seeded in TMEM (16 warp arrivals)
-  uint64_t* hacc_full = bars + 10;         // GEMM1(j) complete -> TMEM H readable
+  uint8_t* sW1 = sH + kHBytes;
+  uint8_t* sW2 = sW1 + kS1 * kS1Bytes;
+  float* sStat = reinterpret_cast<float*>(sW2 + kS2 * kS2Bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW2 + kS2 * kS2Bytes + kStatBytes);
+  uint64_t* w1_full = bars;                // [3]
+  uint64_t* w1_empty = bars + 3;           // [3]
+  uint64_t* w2_full = bars + 6;            // [2]
+  uint64_t* w2_empty = bars + 8;           // [2]
+  uint64_t* a_full = bars + 10;            // LN(x) operand written and x + b2 seeded in TMEM (16 warp arrivals)
+  uint64_t* hacc_full = bars + 11;         // GEMM1(j) complete -> TMEM H readable
   uint64_t* hacc_empty = bars + 12;        // epilogue finished reading TMEM H (16 warp arrivals)
-  uint64_t* hs_full = bars + 14;           // SMEM H written (16 warp arrivals)
-  uint64_t* hs_empty = bars + 16;          // GEMM2 finished reading SMEM H
-  uint64_t* y_full = bars + 18;            // all MMAs of the tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* hs_full = bars + 13;           // SMEM H written (16 warp arrivals)
+  uint64_t* hs_empty = bars + 14;          // GEMM2 finished reading SMEM H
+  uint64_t* y_full = bars + 15;            // all MMAs of the tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CM > 1 ? (int)cluster_ctarank() : 0;
@@ -119,14 +113,15 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1), tma_prefetch_desc(&tmW2), tma_prefetch_desc(&tmOut);
-    for (int s = 0; s < kSlots; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], CM);
+    for (int s = 0; s < kS1; ++s) mbar_init(&w1_full[s], 1), mbar_init(&w1_empty[s], CM);
+    for (int s = 0; s < kS2; ++s) mbar_init(&w2_full[s], 1), mbar_init(&w2_empty[s], CM);
     mbar_init(a_full, kEpiWarps);
     mbar_init(hacc_full, 1), mbar_init(hacc_empty, kEpiWarps);
     mbar_init(hs_full, kEpiWarps), mbar_init(hs_empty, 1);
     mbar_init(y_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -136,119 +131,119 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (weights only)
+    // ------------------------------------------------------------------ TMA producer of W1 (GEMM1's ring)
     if (lane == 0) {
       int slot = 0;
-      uint32_t wphase = 0;
-      auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
-      auto load_w1 = [&](int j) {  // W1 rows [128j, 128j+128): six k-blocks, one slot each
-        for (int kb = 0; kb < D / 64; ++kb) {
-          mbar_wait(&w_empty[slot], wphase ^ 1);
-          mbar_arrive_expect_tx(&w_full[slot], 16384);
-          uint8_t* dst = sW + slot * kSlotBytes;
-          if (CM == 1) {
-            tma_load_2d(dst, &tmW1, &w_full[slot], kb * 64, j * HC);
-          } else {  // each CTA fetches 64 of the 128 rows and multicasts them
-            tma_load_2d_mc(dst + rank * 8192, &tmW1, &w_full[slot], kb * 64, j * HC + rank * 64, kMask);
-          }
-          next();
-        }
-      };
-      auto load_w2 = [&](int j) {  // W2[:, 128j : 128j+128): per k-block two N-halves of 192 rows, one slot each
-        for (int kb = 0; kb < HC / 64; ++kb)
-          for (int nh = 0; nh < 2; ++nh) {
-            mbar_wait(&w_empty[slot], wphase ^ 1);
-            mbar_arrive_expect_tx(&w_full[slot], kSlotBytes);
-            uint8_t* dst = sW + slot * kSlotBytes;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < super_m; t += num_clusters)
+        for (int j = 0; j < NCH; ++j)
+          for (int kb = 0; kb < D / 64; ++kb) {  // W1 rows [128j, 128j+128), k-block kb
+            mbar_wait(&w1_empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&w1_full[slot], kS1Bytes);
+            uint8_t* dst = sW1 + slot * kS1Bytes;
             if (CM == 1) {
-              tma_load_2d(dst, &tmW2, &w_full[slot], j * HC + kb * 64, nh * 192);
-            } else {
-              tma_load_2d_mc(dst + rank * 12288, &tmW2, &w_full[slot], j * HC + kb * 64, nh * 192 + rank * 96, kMask);
+              tma_load_2d(dst, &tmW1, &w1_full[slot], kb * 64, j * HC);
+            } else {  // each CTA fetches 64 of the 128 rows and multicasts them
+              tma_load_2d_mc(dst + rank * 8192, &tmW1, &w1_full[slot], kb * 64, j * HC + rank * 64, kMask);
             }
-            next();
+            if (++slot == kS1) slot = 0, ph ^= 1;
           }
-      };
-      for (int t = cluster_id; t < super_m; t += num_clusters) {
-        load_w1(0);
-        for (int j = 0; j < NCH; ++j) {  // the order the MMA warp consumes: GEMM1(j + 1), then GEMM2(j)
-          if (j + 1 < NCH) load_w1(j + 1);
-          load_w2(j);
-        }
-      }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ TMA producer of W2 (GEMM2's ring)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < super_m; t += num_clusters)
+        for (int j = 0; j < NCH; ++j)
+          for (int kb = 0; kb < HC / 64; ++kb)
+            for (int nh = 0; nh < 2; ++nh) {  // W2[:, 128j + 64kb : +64), output rows [192nh, 192nh + 192)
+              mbar_wait(&w2_empty[slot], ph ^ 1);
+              mbar_arrive_expect_tx(&w2_full[slot], kS2Bytes);
+              uint8_t* dst = sW2 + slot * kS2Bytes;
+              if (CM == 1) {
+                tma_load_2d(dst, &tmW2, &w2_full[slot], j * HC + kb * 64, nh * 192);
+              } else {
+                tma_load_2d_mc(dst + rank * 12288, &tmW2, &w2_full[slot], j * HC + kb * 64, nh * 192 + rank * 96, kMask);
+              }
+              if (++slot == kS2) slot = 0, ph ^= 1;
+            }
+    }
+    __syncwarp();
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers: warp 2 = GEMM1, warp 3 = GEMM2
     if (UI || lane == 0) {
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
         if (UI) umma_f16_elect(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
       };
       auto commit = [&](uint64_t* bar) { if (UI) umma_commit_elect(bar); else umma_commit(bar); };
-      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 192);
-      int slot = 0;
-      uint32_t wphase = 0, tphase = 0, hacc_ph = 0, hs_ph = 0;
-      auto next = [&]() { if (++slot == kSlots) slot = 0, wphase ^= 1; };
       auto release = [&](uint64_t* bar) {
         if (CM == 1) commit(bar);
         else if (UI) umma_commit_mc_elect(bar, kMask);
         else umma_commit_mc(bar, kMask);
       };
-      auto gemm1 = [&]() {  // TMEM[384..511] = LN(x) · W1 chunk^T, K = 384: 6 k-blocks x 4 k-steps of M128 N128 K16
-        for (int kb = 0; kb < D / 64; ++kb) {
-          mbar_wait(&w_full[slot], wphase);
+      int slot = 0;
+      uint32_t wph = 0, tph = 0;
+      if (warp == 2) {
+        // GEMM1: TMEM[384..511] = LN(x) · W1 chunk^T, K = 384: 6 k-blocks x 4 k-steps of M128 N128 K16 per chunk
+        constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);
+        uint32_t he_ph = 0;
+        for (int t = cluster_id; t < super_m; t += num_clusters) {
+          mbar_wait(a_full, tph);  // LN(x) is in shared memory
+          tph ^= 1;
           tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(sA + kb * 16384));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma(tmem + 384, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
-          release(&w_empty[slot]);
-          next();
-        }
-        commit(hacc_full);
-      };
-      auto gemm2 = [&]() {  // x_tmem[0..383] += GELU(H chunk) · W2 chunk^T, K = 128: 2 k-blocks x 2 N-halves x 4 k-steps
-        for (int kb = 0; kb < HC / 64; ++kb) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(sH + kb * 16384));
-          for (int nh = 0; nh < 2; ++nh) {
-            mbar_wait(&w_full[slot], wphase);
+          for (int j = 0; j < NCH; ++j) {
+            mbar_wait(hacc_empty, he_ph ^ 1);  // the epilogue holds the previous chunk in registers: TMEM H is free
+            he_ph ^= 1;
             tc_fence_after();
-            const uint64_t bd = umma_desc_sw128(smem_u32(sW + slot * kSlotBytes));
+            for (int kb = 0; kb < D / 64; ++kb) {
+              mbar_wait(&w1_full[slot], wph);
+              tc_fence_after();
+              const uint64_t ad = umma_desc_sw128(smem_u32(sA + kb * 16384));
+              const uint64_t bd = umma_desc_sw128(smem_u32(sW1 + slot * kS1Bytes));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma(tmem + nh * 192, ad + 2 * k, bd + 2 * k, idesc2, 1u);
-            release(&w_empty[slot]);
-            next();
+              for (int k = 0; k < 4; ++k) mma(tmem + 384, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+              release(&w1_empty[slot]);
+              if (++slot == kS1) slot = 0, wph ^= 1;
+            }
+            commit(hacc_full);
           }
         }
-        commit(hs_empty);
-      };
-      for (int t = cluster_id; t < super_m; t += num_clusters) {
-        mbar_wait(a_full, tphase);   // LN(x) in SMEM, x + b2 in TMEM columns 0..383
-        tc_fence_after();
-        gemm1();                     // chunk 0 (TMEM H is free: the previous tile's last chunk was read before its GEMM2)
-        for (int j = 0; j < NCH; ++j) {
-          if (j + 1 < NCH) {
-            mbar_wait(hacc_empty, hacc_ph);  // the epilogue holds chunk j in registers: TMEM H may be overwritten
-            hacc_ph ^= 1;
-            tc_fence_after();
-            gemm1();
-          }
-          mbar_wait(hs_full, hs_ph);         // GELU(H_j) is in shared memory
-          hs_ph ^= 1;
+      } else {
+        // GEMM2: x_tmem[0..383] += GELU(H chunk) · W2 chunk^T, K = 128: 2 k-blocks x 2 N-halves x 4 k-steps of M128 N192
+        constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 192);
+        uint32_t hs_ph = 0;
+        for (int t = cluster_id; t < super_m; t += num_clusters) {
+          mbar_wait(a_full, tph);  // x + b2 is seeded in TMEM columns 0..383
+          tph ^= 1;
           tc_fence_after();
-          gemm2();
+          for (int j = 0; j < NCH; ++j) {
+            mbar_wait(hs_full, hs_ph);  // GELU(H_j) is in shared memory
+            hs_ph ^= 1;
+            tc_fence_after();
+            for (int kb = 0; kb < HC / 64; ++kb) {
+              const uint64_t ad = umma_desc_sw128(smem_u32(sH + kb * 16384));
+              for (int nh = 0; nh < 2; ++nh) {
+                mbar_wait(&w2_full[slot], wph);
+                tc_fence_after();
+                const uint64_t bd = umma_desc_sw128(smem_u32(sW2 + slot * kS2Bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma(tmem + nh * 192, ad + 2 * k, bd + 2 * k, idesc2, 1u);
+                release(&w2_empty[slot]);
+                if (++slot == kS2) slot = 0, wph ^= 1;
+              }
+            }
+            commit(hs_empty);
+          }
+          commit(y_full);  // GEMM1's MMAs precede GEMM2(11) through the epilogue, so this covers the whole tile
         }
-        // the last chunk's hacc_empty arrival is consumed here so that the phases stay aligned across tiles
-        mbar_wait(hacc_empty, hacc_ph);
-        hacc_ph ^= 1;
-        commit(y_full);
-        tphase ^= 1;
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ 16 epilogue warps
-    const int ew = warp - 2;                 // 0..15
+    const int ew = warp - 4;                 // 0..15
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
     const int sub = ew >> 2;                 // 0..3: which of the 4 warps of this quarter (= its 32-column slice of a chunk)
     const int r_in_tile = quarter * 32 + lane;
@@ -262,43 +257,79 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       const int tm = t * CM + rank;
       const int row = tm * BM + r_in_tile;
       const bool row_ok = row < args.M;
-      // ---- prologue, pass A: row statistics, one warp per row (8 rows per warp), coalesced 8-byte loads, two-pass variance
-      for (int rr = 0; rr < 8; ++rr) {
-        const int rt = ew * 8 + rr;
-        const long grow = (long)tm * BM + rt;
-        float v[12];
-        float s = 0.f;
-        if (grow < args.M) {
+      // ---- prologue, pass A: row statistics, one warp per row (8 rows per warp), coalesced 8-byte loads, two-pass variance.
+      // All 24 loads of the warp's 8 rows are issued before the first use (one memory round trip instead of eight) and the
+      // eight shuffle reductions advance in lock-step.
+      {
+        uint2 q[8][3];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const long grow = (long)tm * BM + ew * 8 + rr;
           const bf16* xr = args.x + grow * args.ldx;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(xr + (lane + i * 32) * 4));
-            v[i * 4 + 0] = bf16_lo(q.x), v[i * 4 + 1] = bf16_hi(q.x), v[i * 4 + 2] = bf16_lo(q.y), v[i * 4 + 3] = bf16_hi(q.y);
-            s += v[i * 4] + v[i * 4 + 1] + v[i * 4 + 2] + v[i * 4 + 3];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 12; ++i) v[i] = 0.f;
+          for (int i = 0; i < 3; ++i)
+            q[rr][i] = grow < args.M ? __ldg(reinterpret_cast<const uint2*>(xr + (lane + i * 32) * 4)) : make_uint2(0u, 0u);
         }
-        const float mu = warp_sum(s) * (1.0f / D);
-        float sq = 0.f;
+        float s[8], sq[8];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) sq += (v[i] - mu) * (v[i] - mu);
-        const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + args.eps);
-        if (lane == 0) sStat[rt * 2] = mu, sStat[rt * 2 + 1] = rs;
+        for (int rr = 0; rr < 8; ++rr) {
+          s[rr] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            s[rr] += bf16_lo(q[rr][i].x) + bf16_hi(q[rr][i].x) + bf16_lo(q[rr][i].y) + bf16_hi(q[rr][i].y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const float mu = s[rr] * (1.0f / D);
+          s[rr] = mu;
+          sq[rr] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float a = bf16_lo(q[rr][i].x) - mu, b = bf16_hi(q[rr][i].x) - mu;
+            const float c = bf16_lo(q[rr][i].y) - mu, d = bf16_hi(q[rr][i].y) - mu;
+            sq[rr] += a * a + b * b + c * c + d * d;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
+        if (lane < 8) {
+          float mu = s[0], v = sq[0];
+#pragma unroll
+          for (int rr = 1; rr < 8; ++rr)
+            if (lane == rr) mu = s[rr], v = sq[rr];
+          sStat[(ew * 8 + lane) * 2] = mu;
+          sStat[(ew * 8 + lane) * 2 + 1] = rsqrtf(v * (1.0f / D) + args.eps);
+        }
       }
       epi_barrier();
       // ---- pass B: this thread's row, columns [sub * 96, sub * 96 + 96)
       const float mean = sStat[r_in_tile * 2], rstd = sStat[r_in_tile * 2 + 1];
       const bf16* xrow = args.x + (long)row * args.ldx + sub * 96;
-      // normalised row -> swizzled A operand; x + b2 -> TMEM (fp32) in three batches of 32 columns
+      // normalised row -> swizzled A operand; x + b2 -> TMEM (fp32) in three batches of 32 columns; the x chunks of batch
+      // b + 1 are in flight while batch b is processed
+      uint4 xq[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xq[0][i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(xrow + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int batch = 0; batch < 3; ++batch) {
+        if (batch + 1 < 3) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            xq[(batch + 1) & 1][i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(xrow + (batch + 1) * 32 + i * 8))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+        }
         uint32_t seed[32];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int col = sub * 96 + batch * 32 + i * 8;
-          const uint4 q = row_ok ? __ldg(reinterpret_cast<const uint4*>(xrow + batch * 32 + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
+          const uint4 q = xq[batch & 1][i];
           const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
           const float4 lw0 = __ldg(reinterpret_cast<const float4*>(args.ln_w + col));
           const float4 lw1 = __ldg(reinterpret_cast<const float4*>(args.ln_w + col + 4));
@@ -328,8 +359,7 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
+      mbar_arrive_elect(a_full);
 
       // ---- hidden chunks: every warp takes its 32 columns of every chunk
       for (int j = 0; j < NCH; ++j) {
@@ -340,13 +370,23 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         tmem_ld32(tmem + lane_base + 384 + sub * 32, r0);
         tmem_ld_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hacc_empty);
+        mbar_arrive_elect(hacc_empty);  // TMEM H is free: GEMM1(j + 1) may start while this chunk is in the GELU below
+        // ptxas hoists the (register-only) GELU arithmetic above the arrive unless something the arithmetic needs is ordered
+        // after it: the bias slice is loaded behind a CTA fence, which loads cannot cross (v1 / v3 profiles: the release came
+        // ~300 instructions late and GEMM1(j + 1) waited for GELU(j)).
+        __threadfence_block();
         const float* bias = args.b1 + j * HC + sub * 32;
+        float4 bv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(bv[c].x), "=f"(bv[c].y), "=f"(bv[c].z), "=f"(bv[c].w)
+                       : "l"(bias + c * 4)
+                       : "memory");
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+          const float4 bb = bv[c >> 2];
           const float2 g0 = gelu2(make_float2(__uint_as_float(r0[c]) + bb.x, __uint_as_float(r0[c + 1]) + bb.y));
           const float2 g1 = gelu2(make_float2(__uint_as_float(r0[c + 2]) + bb.z, __uint_as_float(r0[c + 3]) + bb.w));
           pk[c / 2] = pack_bf16(g0.x, g0.y), pk[c / 2 + 1] = pack_bf16(g1.x, g1.y);
@@ -362,8 +402,7 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
               make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
         }
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hs_full);
+        mbar_arrive_elect(hs_full);
       }
       // ---- final epilogue: TMEM columns 0..383 already hold x + b2 + FF(LN(x)); 3 chunks of 32 columns per warp
       mbar_wait(y_full, tphase);
@@ -401,7 +440,7 @@ ff_block_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
 
   tc_fence_before();
   if (CM > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -411,7 +450,7 @@ int ff_uniform_issue() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("N1_FF_UI");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;   // validated: tests/test_ops_gpu.py::test_ff_block with N1_FF_UI=1, 7 % faster (profiles/)
   }
   return v;
 }

@@ -11,6 +11,7 @@
 // dinov2_layers/{attention.py L46-48, mlp.py L30-32, patch_embed.py L65} and the Qwen2.5-VL blocks.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -52,13 +53,17 @@ struct GemmArgs {
   int out_fp32;
   int rows_per_group, group_stride, group_offset;
   const float* row_add;
+  int raster_g;   // M (super-)tiles per raster group (decode_tile)
   int tma_store;  // bf16 output tile goes registers -> smem staging -> cp.async.bulk.tensor store (full-sector writes)
 };
 
-// Grouped rasterisation: consecutive tile ids walk 8 M-tiles before moving to the next N-tile, so the CTAs
-// resident at one time share few W panels and few A panels (both stay L2-resident).
-__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-  constexpr int G = 8;
+// Grouped rasterisation: consecutive tile ids walk G M-tiles before moving to the next N-tile, so the CTAs resident at
+// one time share few W panels, and the A panels of a group stay L2-resident while the group sweeps all N tiles.  DRAM
+// traffic ~ W bytes x (tiles_m / G) + A bytes: G = 8 re-read W 19 times for the LLM gate/up GEMM (N = 37888: 5.3 GB per
+// launch for 0.41 GB algorithmic, profiles/r1_ncu_full_gemm_llm_v0_summary.txt), so G now grows until the group's A
+// panels fill about 28 MB (measured optimum: 64 MB groups are not L2-resident next to the streaming W -- the two L2
+// partitions duplicate lines -- and 16 MB re-reads W more often; profiles/README.md).
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int G, int& tm, int& tn) {
   const int per_group = G * tiles_n;
   const int g = tile / per_group;
   const int first_m = g * G;
@@ -71,7 +76,9 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
 // CM = cluster size along M.  With CM > 1 the CM CTAs of a cluster work on CM vertically adjacent tiles of the same
 // N panel: every CTA fetches 1/CM of the W tile and multicasts it to its peers, which divides the L2 -> SMEM traffic
 // for W by CM (the short-K GEMMs of the path are L2-bandwidth-bound, profiles/r1_ncu_small_v0_summary.txt).
-template <int BN, int CM>
+// UI ("uniform issue"): the MMA warp runs its loop with all 32 lanes and an elected lane issues, so the descriptors stay
+// in uniform registers instead of being moved there (R2UR + ELECT + R2UR.BROADCAST) before every tcgen05.mma.
+template <int BN, int CM, bool UI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
@@ -130,7 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int tm, tn;
-        decode_tile(tile, super_m, args.tiles_n, tm, tn);
+        decode_tile(tile, super_m, args.tiles_n, args.raster_g, tm, tn);
         tm = tm * CM + rank;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -153,7 +160,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (UI || lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -171,18 +178,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (UI) umma_f16_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (CM == 1)
-            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-          else
-            umma_commit_mc(&empty[stage], kMask);
+          if (CM == 1) {  // smem slot reusable once these MMAs have read it
+            if (UI) umma_commit_elect(&empty[stage]); else umma_commit(&empty[stage]);
+          } else {
+            if (UI) umma_commit_mc_elect(&empty[stage], kMask); else umma_commit_mc(&empty[stage], kMask);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete
+        if (UI) umma_commit_elect(&tfull[acc]); else umma_commit(&tfull[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -201,7 +210,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int sbuf = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int tm, tn;
-      decode_tile(tile, super_m, args.tiles_n, tm, tn);
+      decode_tile(tile, super_m, args.tiles_n, args.raster_g, tm, tn);
       tm = tm * CM + rank;
       const int row = tm * BM + quarter * 32 + lane;
       const bool row_ok = row < args.M;
@@ -439,13 +448,13 @@ CUtensorMap make_map(const bf16* ptr, long rows, long cols, long ld, int box_row
   return m;
 }
 
-template <int BN, int CM>
+template <int BN, int CM, bool UI>
 void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   static std::once_flag once;
   static int max_clusters = 0;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(gemm_kernel<BN, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaFuncSetAttribute(gemm_kernel<BN, CM, UI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     max_clusters = device_sm_count() / CM;
     if (CM > 1) {
       cudaLaunchConfig_t cfg = {};
@@ -455,11 +464,28 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
       at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
       cfg.attrs = &at, cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, CM>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, CM, UI>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
     }
   });
   a.tiles_m = (M + BM - 1) / BM;
   a.tiles_n = (N + BN - 1) / BN;
+  {
+    // raster group: as many (super-)tiles of A as fit ~28 MB of L2; only matters when W does not fit L2
+    const long panel = (long)BM * CM * K * 2;
+    const long w_bytes = (long)N * K * 2;
+    int g = 8;
+    static long budget_mb = -1;  // N1_GEMM_RASTER_MB: L2 budget for the A panels of a raster group
+    if (budget_mb < 0) {
+      const char* e = getenv("N1_GEMM_RASTER_MB");
+      budget_mb = e ? atol(e) : 28;
+    }
+    // (L2 eviction-priority hints on the TMA loads -- W evict-first, A evict-last -- were measured and made it worse: the
+    // concurrent clusters that share a W tile lose it before they read it; profiles/README.md, raster experiments)
+    if (w_bytes > (64L << 20)) g = (int)std::max<long>(2, (budget_mb << 20) / panel);
+    const int super_m = (a.tiles_m + CM - 1) / CM;
+    a.raster_g = g < super_m ? g : super_m;
+    if (a.raster_g < 1) a.raster_g = 1;
+  }
   CUtensorMap tmA = make_map(A, M, K, lda, BM);
   CUtensorMap tmB = make_map(W, N, K, ldw, BN / CM);
   CUtensorMap tmC = tmA;  // placeholder when the direct-store epilogue is used
@@ -470,7 +496,7 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   const int super_tiles = ((a.tiles_m + CM - 1) / CM) * a.tiles_n;
   const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
   if (CM == 1) {
-    gemm_kernel<BN, CM><<<clusters, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, a);
+    gemm_kernel<BN, CM, UI><<<clusters, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmC, a);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CM), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes;
@@ -479,12 +505,13 @@ void launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = CM, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
     cfg.attrs = &at, cfg.numAttrs = 1;
-    N1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CM>, tmA, tmB, tmC, a));
+    N1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CM, UI>, tmA, tmB, tmC, a));
   }
   N1_CUDA(cudaGetLastError());
 }
 
 std::atomic<int> g_cluster_m{2};
+std::atomic<int> g_uniform_issue{-1};  // N1_GEMM_UI: 1 = warp-uniform MMA issue everywhere, 0 = nowhere, default (-1) = K >= 1024
 std::atomic<int> g_tma_store{1};  // developer knob (N1_GEMM_TMA_STORE=0 selects the direct-store epilogue)  // developer knob (N1_GEMM_CLUSTER=1 disables the multicast path)
 
 // ---- profiling state
@@ -578,6 +605,7 @@ int device_sm_count() {
   if (!sms) {
     if (const char* e = getenv("N1_GEMM_CLUSTER")) g_cluster_m = atoi(e);
     if (const char* e = getenv("N1_GEMM_TMA_STORE")) g_tma_store = atoi(e);
+    if (const char* e = getenv("N1_GEMM_UI")) g_uniform_issue = atoi(e);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -628,16 +656,23 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ld
   if (cost(64) < best) bn = 64;
   // clusters of 2 along M (W multicast) whenever there are at least two M tiles to pair up
   const bool pair = tm >= 2 && g_cluster_m.load() >= 2;
+  // uniform issue pays where the K loop is long (decoder / vision-tower shapes: -1.5 .. -3 % per stage, A/B in
+  // profiles/README.md); the 384-wide System-1 shapes were neutral to slightly slower, so they keep the one-lane loop
+  const int ui_mode = g_uniform_issue.load();
+  const bool ui = ui_mode == 1 || (ui_mode < 0 && K >= 1024);
+#define N1_LAUNCH(BN_, CM_)                                                       \
+  do {                                                                            \
+    if (ui) launch<BN_, CM_, true>(A, lda, W, ldw, M, N, K, a, stream);           \
+    else launch<BN_, CM_, false>(A, lda, W, ldw, M, N, K, a, stream);             \
+  } while (0)
   if (bn == 256) {
-    if (pair) launch<256, 2>(A, lda, W, ldw, M, N, K, a, stream);
-    else launch<256, 1>(A, lda, W, ldw, M, N, K, a, stream);
+    if (pair) N1_LAUNCH(256, 2); else N1_LAUNCH(256, 1);
   } else if (bn == 128) {
-    if (pair) launch<128, 2>(A, lda, W, ldw, M, N, K, a, stream);
-    else launch<128, 1>(A, lda, W, ldw, M, N, K, a, stream);
+    if (pair) N1_LAUNCH(128, 2); else N1_LAUNCH(128, 1);
   } else {
-    if (pair) launch<64, 2>(A, lda, W, ldw, M, N, K, a, stream);
-    else launch<64, 1>(A, lda, W, ldw, M, N, K, a, stream);
+    if (pair) N1_LAUNCH(64, 2); else N1_LAUNCH(64, 1);
   }
+#undef N1_LAUNCH
   if (prof) {
     cudaEventRecord(ev.b, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);

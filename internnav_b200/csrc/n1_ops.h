@@ -112,8 +112,13 @@ struct AttnParams {
   int max_seq_q;         // upper bound on query length (grid sizing) when varlen
   const int* k_len;      // optional [batch_kv] device: slotted K/V (a KV cache) -- sequence kb occupies rows
   int k_slot;            //   [kb * k_slot, kb * k_slot + k_len[kb]); overrides cu_k / seq_k
+  long total_rows;       // optional: rows of the packed q / k / v buffers (var-len self-attention); > 0 lets head_dim 128
+                         //   sequences of <= 320 tokens take the tcgen05 kernel (attention_tc.cu), which needs it for TMA
 };
 void attention(const AttnParams& p, cudaStream_t stream);
+// tcgen05 / TMEM / TMA attention for head_dim 128, var-len self-attention with <= 320 keys per sequence (attention_tc.cu)
+bool attention_tc_supported(const AttnParams& p);
+void attention_tc128(const AttnParams& p, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------- fused decoder blocks
 // FF block of the NavDP decoder layer in one kernel (ff_block.cu): out = x + W2 GELU(W1 LayerNorm(x) + b1) + b2 with the

@@ -413,7 +413,7 @@ size_t S2Model::llm_impl(Carver c, const LlmPlan& p, const bf16* image_feats, bf
     a.q = qkv, a.k = qkv + (long)dims.heads * hd, a.v = qkv + (long)(dims.heads + dims.kv_heads) * hd, a.o = att;
     a.ldq = a.ldk = a.ldv = qkv_n, a.ldo = H;
     a.heads_q = dims.heads, a.heads_kv = dims.kv_heads, a.hd = hd;
-    a.batch = p.B, a.cu_q = a.cu_k = p.cu, a.max_seq_q = p.max_len;
+    a.batch = p.B, a.cu_q = a.cu_k = p.cu, a.max_seq_q = p.max_len, a.total_rows = T;
     a.kv_div = 1, a.causal = 1, a.scale = 1.0f / sqrtf((float)hd);
     attention(a, s);
     GemmEpilogue res;

@@ -77,6 +77,17 @@ def _worker(rank, world, port, q):
     gb.all_reduce(async_op=True).wait()
     ok = all(torch.equal(gb.grads[n], ref[n]) for n in ref)
     worst = max(float((gb.grads[n] - ref[n]).abs().max()) for n in ref)
+    # the split exchange of the training step: every bucket but the one holding the LAST-arriving gradient first, that one
+    # afterwards (DualSystemTrainer.step overlaps the first part with the System-2 backward) -- same result
+    gb2 = GradientBuckets(OrderedDict((n, (tuple(p.shape), p.dtype)) for n, p in net.named_parameters()), "cpu",
+                          bucket_cap_mb=1)
+    for n, g in local.items():
+        gb2.grads[n].copy_(g)
+    late = gb2.bucket_of("a.weight")
+    gb2.all_reduce(async_op=True, skip=(late,))
+    gb2.all_reduce(async_op=True, only=(late,), append=True)
+    gb2.wait()
+    ok = ok and all(torch.equal(gb2.grads[n], ref[n]) for n in ref)
     if rank == 0:
         q.put((ok, worst, len(gb.buffers)))
     dist.barrier()

@@ -1,5 +1,7 @@
 """Kernel-level parity (through the C ABI) against fp32 PyTorch references of the same op."""
 import math
+
+import numpy as np
 import os
 
 import pytest
@@ -308,3 +310,34 @@ def test_gemm_skinny(L, M, N, K, act, bias, res):
     # and against the tcgen05 GEMM on the same operands: same epilogue order, so agreement to bf16 rounding
     main = L.gemm(a, w, bias=b, residual=r, act=act)
     assert _rel(out, main) < 4e-3, _rel(out, main)
+
+
+@pytest.mark.parametrize("lens,causal", [([304] * 4, True), ([304, 300, 129, 128, 1, 257, 320, 64, 17], True),
+                                         ([320, 200, 96], False), ([304] * 64, True)])
+def test_attention_tcgen05_hd128(L, lens, causal):
+    """Decoder-prefill attention on tcgen05 (attention_tc.cu): var-len GQA 28 / 4, head_dim 128, packed q|k|v rows with the
+    decoder's row stride; against fp32 PyTorch per sequence and against the mma.sync kernel it replaces."""
+    torch.manual_seed(len(lens) + sum(lens))
+    Hq, Hkv, hd = 28, 4, 128
+    T = sum(lens)
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * hd, device="cuda").bfloat16()
+    q, k, v = qkv[:, :Hq * hd], qkv[:, Hq * hd:(Hq + Hkv) * hd], qkv[:, (Hq + Hkv) * hd:]
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device="cuda")
+    o, used = L.attention_varlen(q, k, v, Hq, Hkv, hd, cu, max(lens), causal=causal)
+    assert used, "the tcgen05 kernel should take this shape"
+    old = L.attention(q, k, v, Hq, Hkv, hd, len(lens), 0, 0, cu_q=cu, cu_k=cu, max_seq_q=max(lens), causal=causal)
+    s = 0
+    worst = 0.0
+    for n in lens[:12]:
+        sl = slice(s, s + n)
+        qh = q[sl].float().view(n, Hq, hd).transpose(0, 1)
+        kh = k[sl].float().view(n, Hkv, hd).transpose(0, 1).repeat_interleave(Hq // Hkv, dim=0)
+        vh = v[sl].float().view(n, Hkv, hd).transpose(0, 1).repeat_interleave(Hq // Hkv, dim=0)
+        sc = qh @ kh.transpose(-1, -2) * hd ** -0.5
+        if causal:
+            sc = sc.masked_fill(torch.triu(torch.ones(n, n, dtype=torch.bool, device="cuda"), 1), float("-inf"))
+        ref = (sc.softmax(-1) @ vh).transpose(0, 1).reshape(n, Hq * hd)
+        worst = max(worst, _rel(o[sl], ref))
+        s += n
+    assert worst < 8e-3, worst
+    assert _rel(o, old) < 8e-3
