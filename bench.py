@@ -544,7 +544,8 @@ def run_ours_train(args, wl):
     latent = s2_sd["model.latent_queries"].float()
     del s2_sd
     torch.cuda.empty_cache()
-    tr = DualSystemTrainer(model, s1_sd, latent, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
+    tr = DualSystemTrainer(model, s1_sd, latent, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0,
+                           graph_s1=os.environ.get("N1_TRAIN_GRAPH", "1") != "0")
     B, f = wl["B"], wl["f"]
     sets = _train_batches(wl, rank, 3)
     barrier, timed = _timing_tools(dev, world)
@@ -593,6 +594,20 @@ def run_ours_train(args, wl):
     torch.cuda.synchronize()
     prof = _lib.prof_read()
     _lib.prof_enable(False)
+    # phase breakdown of one step: device time (CUDA events) next to the host wall clock of the same step -- the System-1
+    # schedule is driven from Python (one ctypes call per kernel), so a wall clock well above the device time = host-bound
+    tr.profile_phases = True
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_resident()
+    t_issue = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+    t_wall = (time.perf_counter() - t0) * 1e3
+    phases = tr.phase_ms()
+    tr.profile_phases = False
+    if phases is not None:
+        phases["host_issue_ms"] = t_issue
+        phases["wall_ms"] = t_wall
     fl = dual_flops_per_env(dict(wl, Ns=32))
     D = 384
     vit_s = 12 * (24 * 257 * D * D + 4 * 257 * 257 * D) + 2 * 256 * 588 * D
@@ -614,12 +629,13 @@ def run_ours_train(args, wl):
     _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
             {"seq_len": wl["S"], "frames_per_episode": f, "global_batch": world * B, "trainable_params": n_grad,
              "optimizer": "fused AdamW (fp32 masters), max_grad_norm 1.0, dropout off", "launches_are": "per step",
+             "s1_launch_mode": "CUDA graph replay" if tr.graph_s1 else "eager (one ctypes call per kernel)",
              "weights": "random-init Qwen2.5-VL-7B shapes (frozen) + NavDP (trainable)",
              "prompts": "3 rotating batches with different prompts: plan creation inside the timed region"},
             {"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
              "api": "DualSystemTrainer.step(collated batch, noise, timesteps) -> loss; pinned host batch"},
             algo, unit="episodes/s", metric="InternVLA-N1 DDP training step, episodes/sec",
-            extra_top={"allreduce": allreduce})
+            extra_top={"allreduce": allreduce, "phase_ms": phases})
 
 
 def run_ours_denoise(args, wl):

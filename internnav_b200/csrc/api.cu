@@ -127,6 +127,26 @@ int n1_s1_load(n1_handle h, const n1_s1_dims* d, const n1_tensor_desc* tensors, 
   });
 }
 
+int n1_navdp_policy_load(n1_handle h, const n1_navdp_policy_dims* d, const n1_tensor_desc* tensors, int n, void* stream) {
+  return guard([&] {
+    use(h);
+    if (!d || !tensors || n <= 0) throw Error(N1_ERR_ARG, "n1_navdp_policy_load: null dims/tensors");
+    S1Dims dims;
+    dims.D = d->token_dim, dims.heads = d->heads, dims.layers = d->layers, dims.T = d->predict_size;
+    dims.frames = d->memory_size, dims.frames_depth = d->depth_frames, dims.goal_slots = d->goal_slots;
+    dims.ddpm_steps = d->ddpm_steps, dims.standalone = 1, dims.vlm_dim = 0, dims.n_query = 0;
+    h->s1.load(to_source(tensors, n), dims, S(stream));
+  });
+}
+
+int n1_navdp_critic(n1_handle h, void* ws, size_t ws_bytes, const float* traj, const void* rgbd, float* critic, int B, int Ns,
+                    int T, void* stream) {
+  return guard([&] {
+    use(h);
+    h->s1.navdp_critic(ws, ws_bytes, traj, B16(rgbd), critic, B, Ns, T, S(stream));
+  });
+}
+
 size_t n1_workspace_bytes(n1_handle h, int op, int B, int Ns, int T) {
   size_t r = 0;
   guard([&] {

@@ -10,7 +10,7 @@ namespace {
 // ---------------------------------------------------------------------------------- DINOv2 patchify
 // navdp_backbone.py L159-166 (HWC -> CHW, ImageNet normalise) + patch_embed.py L69-81 (Conv2d k=14,s=14 == GEMM
 // over im2col rows).  Output row = img * 256 + py * 16 + px, column = c * 196 + ky * 14 + kx, zero padded to ldk.
-__global__ void patchify_rgb_kernel(const float* __restrict__ img, bf16* __restrict__ out, int n_img, int ldk) {
+__global__ void patchify_rgb_kernel(const float* __restrict__ img, bf16* __restrict__ out, int n_img, int ldk, int exact) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)n_img * 256 * ldk;
   if (idx >= total) return;
@@ -21,8 +21,12 @@ __global__ void patchify_rgb_kernel(const float* __restrict__ img, bf16* __restr
     const int c = col / 196, k = col % 196, ky = k / 14, kx = k % 14;
     const int im = row / 256, p = row % 256, py = p / 16, px = p % 16;
     // bf16 roundings of the ImageNet mean/std: the reference holds these constants in bf16 (navdp_backbone.py L126-127)
-    const float mean = c == 0 ? 0.484375f : (c == 1 ? 0.455078125f : 0.40625f);
-    const float stdv = c == 0 ? 0.228515625f : (c == 1 ? 0.2236328125f : 0.224609375f);
+    float mean = c == 0 ? 0.484375f : (c == 1 ? 0.455078125f : 0.40625f);
+    float stdv = c == 0 ? 0.228515625f : (c == 1 ? 0.2236328125f : 0.224609375f);
+    if (exact) {  // fp32 constants of the stand-alone RGBDBackbone
+      mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+      stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    }
     const float x = img[(((long)im * 224 + py * 14 + ky) * 224 + px * 14 + kx) * 3 + c];
     v = (x - mean) / stdv;
   }
@@ -123,7 +127,7 @@ __global__ void embed_actions_kernel(const float* __restrict__ xt, const float* 
 // emb = [sin(t f), cos(t f)]).  first_slot/num_slots restrict the update to the time token inside the step loop.
 __global__ void build_cond_kernel(const int* __restrict__ tsteps, int t_scalar, const bf16* __restrict__ goal,
                                   const bf16* __restrict__ rgbd, const float* __restrict__ cpe,
-                                  bf16* __restrict__ cond, int B, int Mtok, int first_slot, int num_slots) {
+                                  bf16* __restrict__ cond, int B, int Mtok, int first_slot, int num_slots, int goal_slots) {
   constexpr int D = 384;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * num_slots * D) return;
@@ -136,10 +140,11 @@ __global__ void build_cond_kernel(const int* __restrict__ tsteps, int t_scalar, 
     const int j = d % 192;
     const float f = expf((float)j * -(logf(10000.0f) / 191.0f));
     v = d < 192 ? sinf(t * f) : cosf(t * f);
-  } else if (slot == 1) {
-    v = __bfloat162float(goal[(long)b * D + d]);
+  } else if (slot <= goal_slots) {
+    v = goal ? __bfloat162float(goal[(long)b * D + d]) : 0.f;
   } else {
-    v = __bfloat162float(rgbd[((long)b * (Mtok - 2) + slot - 2) * D + d]);
+    const int first_mem = 1 + goal_slots;
+    v = __bfloat162float(rgbd[((long)b * (Mtok - first_mem) + slot - first_mem) * D + d]);
   }
   cond[((long)b * Mtok + slot) * D + d] = __float2bfloat16(v + cpe[slot * D + d]);
 }
@@ -208,11 +213,61 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict
 
 inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
 
+
+// Critic head of the stand-alone NavDP policy (navdp_policy.py L183-186): LayerNorm (eps 1e-5) of every row, mean over the T
+// rows of a sample, dot with critic_head.weight, + bias.  One warp per sample; D = 384 (12 values per lane).
+__global__ void __launch_bounds__(256) critic_head_kernel(const bf16* __restrict__ h, const float* __restrict__ lw,
+                                                          const float* __restrict__ lb, const float* __restrict__ cw,
+                                                          const float* __restrict__ cb, long samples, int T,
+                                                          float* __restrict__ out) {
+  constexpr int D = 384;
+  const long smp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (smp >= samples) return;
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const bf16* xr = h + (smp * T + t) * D;
+    float v[12];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint2 q = *reinterpret_cast<const uint2*>(xr + (lane + i * 32) * 4);
+      v[i * 4 + 0] = bf16_lo(q.x), v[i * 4 + 1] = bf16_hi(q.x), v[i * 4 + 2] = bf16_lo(q.y), v[i * 4 + 3] = bf16_hi(q.y);
+      s += v[i * 4] + v[i * 4 + 1] + v[i * 4 + 2] + v[i * 4 + 3];
+    }
+    const float mean = warp_sum(s) / D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sq += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) / D + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (lane + i * 32) * 4 + j;
+        acc[i * 4 + j] += (v[i * 4 + j] - mean) * rstd * lw[c] + lb[c];
+      }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dot += acc[i * 4 + j] * cw[(lane + i * 32) * 4 + j];
+  dot = warp_sum(dot) / T;
+  if (lane == 0) out[smp] = dot + cb[0];
+}
+
+__global__ void fill_int_kernel(int* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 }  // namespace
 
-void patchify_rgb(const float* img, bf16* out, int n_img, int ldk, cudaStream_t s) {
+void patchify_rgb(const float* img, bf16* out, int n_img, int ldk, cudaStream_t s, bool exact_norm) {
   const long total = (long)n_img * 256 * ldk;
-  patchify_rgb_kernel<<<nblk(total, 256), 256, 0, s>>>(img, out, n_img, ldk);
+  patchify_rgb_kernel<<<nblk(total, 256), 256, 0, s>>>(img, out, n_img, ldk, exact_norm ? 1 : 0);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
@@ -245,15 +300,26 @@ void embed_actions(const float* xt, const float* w, const float* bias, const flo
   N1_CUDA(cudaGetLastError());
 }
 void build_cond(const int* tsteps, int t_scalar, const bf16* goal, const bf16* rgbd, const float* cpe, bf16* cond, int B,
-                int Mtok, int first_slot, int num_slots, cudaStream_t s) {
+                int Mtok, int first_slot, int num_slots, cudaStream_t s, int goal_slots) {
   build_cond_kernel<<<nblk((long)B * num_slots * 384, 256), 256, 0, s>>>(tsteps, t_scalar, goal, rgbd, cpe, cond, B, Mtok,
-                                                                        first_slot, num_slots);
+                                                                        first_slot, num_slots, goal_slots);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
 void head_ddpm(const bf16* h, const float* lw, const float* lb, const float* hw, const float* hb, long rows, int mode,
                float* x, const float* noise, float* eps_out, const DdpmCoef& cf, cudaStream_t s) {
   head_kernel<<<nblk(rows * 32, 256), 256, 0, s>>>(h, lw, lb, hw, hb, rows, mode, x, noise, eps_out, cf);
+  prof_count_launch();
+  N1_CUDA(cudaGetLastError());
+}
+void critic_head(const bf16* h, const float* lw, const float* lb, const float* cw, const float* cb, long samples, int T,
+                 float* out, cudaStream_t s) {
+  critic_head_kernel<<<nblk(samples * 32, 256), 256, 0, s>>>(h, lw, lb, cw, cb, samples, T, out);
+  prof_count_launch();
+  N1_CUDA(cudaGetLastError());
+}
+void fill_int(int* p, int value, int n, cudaStream_t s) {
+  fill_int_kernel<<<nblk(n, 256), 256, 0, s>>>(p, value, n);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }

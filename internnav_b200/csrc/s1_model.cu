@@ -189,14 +189,15 @@ void S1Model::load(const WeightSource& ws, const S1Dims& d, cudaStream_t s) {
   const int D = dims.D;
   N1_CHECK(D == 384, "System-1 kernels are specialised for token_dim 384");
   N1_CHECK(D / dims.heads == 48, "System-1 decoder head_dim must be 48");
-  const int Mq = 16 * dims.frames;
+  const int Mq = dims.mem_tokens();
+  const long slots = dims.frames + dims.depth_frames();   // 256-token image slots of the Q-former memory
   rgb_ = load_vit(ws.sub("rgbd_encoder.rgb_model."), false, s);
   depth_ = load_vit(ws.sub("rgbd_encoder.depth_model."), true, s);
   const WeightSource enc = ws.sub("rgbd_encoder.");
   {
     const long pe_rows = enc.get("former_pe.weight").numel() / D;
-    N1_CHECK(pe_rows >= 2L * dims.frames * 256, "former_pe too small (needs navdp_version > 0 layout)");
-    former_pe_ = enc.f32_rows(arena_, "former_pe.weight", 0, 2L * dims.frames * 256, D, s);
+    N1_CHECK(pe_rows >= slots * 256, "former_pe too small (needs navdp_version > 0 layout)");
+    former_pe_ = enc.f32_rows(arena_, "former_pe.weight", 0, slots * 256, D, s);
     int ld;
     former_query_ = enc.mat(arena_, "former_query.weight", 0, Mq, D, &ld, s);
   }
@@ -205,7 +206,9 @@ void S1Model::load(const WeightSource& ws, const S1Dims& d, cudaStream_t s) {
     former_.push_back(load_dec_layer(enc.sub("former_net.layers." + std::to_string(i) + "."), true, s));
   project_ = load_lin(arena_, enc, "project_layer.weight", "project_layer.bias", 0, D, D, s);
 
-  // goal path: vlm_embed_mlp (navdp.py L94-100) + TokenCompressor (navdp_backbone.py L60-99)
+  // goal path: vlm_embed_mlp (navdp.py L94-100) + TokenCompressor (navdp_backbone.py L60-99); the stand-alone policy has
+  // none (its goal token is point_encoder(goal) or zero, computed by the caller)
+  if (!dims.standalone) {
   vlm0_ = load_lin(arena_, ws, "vlm_embed_mlp.0.weight", "vlm_embed_mlp.0.bias", 0, dims.vlm_dim / 4, dims.vlm_dim, s);
   vlm1_ = load_lin(arena_, ws, "vlm_embed_mlp.2.weight", "vlm_embed_mlp.2.bias", 0, dims.vlm_dim / 8, dims.vlm_dim / 4, s);
   vlm2_ = load_lin(arena_, ws, "vlm_embed_mlp.4.weight", "vlm_embed_mlp.4.bias", 0, D, dims.vlm_dim / 8, s);
@@ -230,12 +233,17 @@ void S1Model::load(const WeightSource& ws, const S1Dims& d, cudaStream_t s) {
     goal_q_ = arena_.alloc_n<bf16>(D);
     linear(gq, qin, D, goal_q_, D, 1, GemmEpilogue(), s);
   }
+  }  // !standalone
 
   // denoiser
   in_w_ = ws.f32(arena_, "input_embed.weight", s);
   in_b_ = ws.f32(arena_, "input_embed.bias", s);
   out_pos_ = ws.f32_rows(arena_, "out_pos_embed", 0, dims.T, D, s);
-  cond_pos_ = ws.f32_rows(arena_, "cond_pos_embed", 0, 2 + Mq, D, s);
+  cond_pos_ = ws.f32_rows(arena_, "cond_pos_embed", 0, dims.cond_tokens(), D, s);
+  if (dims.standalone) {
+    critic_w_ = ws.f32(arena_, "critic_head.weight", s);
+    critic_b_ = ws.f32(arena_, "critic_head.bias", s);
+  }
   dec_.clear();
   kv_all_.N = dims.layers * 2 * D, kv_all_.K = D, kv_all_.ldw = D;
   kv_all_.w = arena_.alloc_n<bf16>((size_t)kv_all_.N * D);
@@ -258,7 +266,8 @@ void S1Model::load(const WeightSource& ws, const S1Dims& d, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ RGB-D encoder
 // Returns the scratch high-water mark (bytes from the start of `c0`'s buffer); launches nothing when dry.
 size_t S1Model::vit_forward(const Vit& v, Carver c, const float* img, bool depth, int n_img, bf16* mem, int slot_base,
-                            cudaStream_t s, bool with_pe) const {
+                            cudaStream_t s, bool with_pe, int frames_per_env) const {
+  if (frames_per_env <= 0) frames_per_env = dims.frames;
   const int D = dims.D;
   const long rows = (long)n_img * 257;
   const int ldk = v.patch.K;
@@ -273,7 +282,7 @@ size_t S1Model::vit_forward(const Vit& v, Carver c, const float* img, bool depth
   if (depth)
     patchify_depth(img, col, n_img, ldk, s);
   else
-    patchify_rgb(img, col, n_img, ldk, s);
+    patchify_rgb(img, col, n_img, ldk, s, dims.standalone != 0);
   {
     GemmEpilogue e;  // x[img, 1 + p, :] = patch + bias + pos[p]
     e.rows_per_group = 256, e.group_stride = 257, e.group_offset = 1, e.row_add = v.pos_patch;
@@ -300,13 +309,14 @@ size_t S1Model::vit_forward(const Vit& v, Carver c, const float* img, bool depth
     e3.gamma = b.ls2, e3.residual = x, e3.ldr = D;
     linear(b.fc2, hid, 4 * D, x, D, (int)rows, e3, s);
   }
-  vit_out(x, mem, v.norm.w, v.norm.b, with_pe ? former_pe_ : nullptr, n_img, dims.frames, slot_base, 2 * dims.frames, s);
+  vit_out(x, mem, v.norm.w, v.norm.b, with_pe ? former_pe_ : nullptr, n_img, frames_per_env, slot_base,
+          dims.frames + dims.depth_frames(), s);
   return c.used();
 }
 
 size_t S1Model::rgbd_impl(Carver c, const float* rgb, const float* depth, bf16* out, int B, cudaStream_t s) const {
-  const int D = dims.D, F = dims.frames, Mq = 16 * F;
-  const long mrows = (long)B * 2 * F * 256;
+  const int D = dims.D, F = dims.frames, Fd = dims.depth_frames(), Mq = dims.mem_tokens();
+  const long mrows = (long)B * (F + Fd) * 256;
   bf16* mem = c.take<bf16>(mrows * D);
   const long qrows = (long)B * Mq;
   bf16* x = c.take<bf16>(qrows * D);
@@ -317,7 +327,7 @@ size_t S1Model::rgbd_impl(Carver c, const float* rgb, const float* depth, bf16* 
   bf16* kv = c.take<bf16>(mrows * 2 * D);
   // the two ViT passes run back to back on one stream and share the scratch after `kv`
   const size_t hi_rgb = vit_forward(rgb_, c, rgb, false, B * F, mem, 0, s);
-  const size_t hi_dep = vit_forward(depth_, c, depth, true, B * F, mem, F, s);
+  const size_t hi_dep = vit_forward(depth_, c, depth, true, B * Fd, mem, F, s, true, Fd);
   const size_t hi = hi_rgb > hi_dep ? hi_rgb : hi_dep;
   if (c.dry()) return hi;
 
@@ -342,7 +352,7 @@ size_t S1Model::rgbd_impl(Carver c, const float* rgb, const float* depth, bf16* 
     AttnParams pc = {};
     pc.q = qkv, pc.k = kv, pc.v = kv + D, pc.o = att;
     pc.ldq = D, pc.ldk = pc.ldv = 2 * D, pc.ldo = D;
-    pc.heads_q = pc.heads_kv = dims.heads, pc.hd = 48, pc.batch = B, pc.seq_q = Mq, pc.seq_k = 2 * F * 256;
+    pc.heads_q = pc.heads_kv = dims.heads, pc.hd = 48, pc.batch = B, pc.seq_q = Mq, pc.seq_k = (F + Fd) * 256;
     pc.kv_div = 1, pc.scale = scale48;
     attention(pc, s);
     linear(L.ca_out, att, D, y, D, (int)qrows, e, s);
@@ -407,10 +417,11 @@ void S1Model::goal_compress(void* ws, size_t ws_bytes, const bf16* latents, bf16
 // ------------------------------------------------------------------------------------------------ denoiser
 struct S1Model::DenoiseBufs {
   bf16 *x, *x2, *ln, *qkv, *att, *hid, *cond, *ckv;
+  int* klen;  // [B] visible memory-token count per environment (critic pass)
 };
 
 S1Model::DenoiseBufs S1Model::carve_denoise(Carver& c, int B, int Ns, int T) const {
-  const int D = dims.D, Mtok = 2 + 16 * dims.frames;
+  const int D = dims.D, Mtok = dims.cond_tokens();
   const long R = (long)B * Ns * T;
   DenoiseBufs d;
   d.x = c.take<bf16>(R * D);
@@ -421,6 +432,7 @@ S1Model::DenoiseBufs S1Model::carve_denoise(Carver& c, int B, int Ns, int T) con
   d.hid = c.take<bf16>(R * 4 * D);
   d.cond = c.take<bf16>((long)B * Mtok * D);
   d.ckv = c.take<bf16>((long)B * Mtok * kv_all_.N);
+  d.klen = c.take<int>(B);
   return d;
 }
 
@@ -429,16 +441,18 @@ S1Model::DenoiseBufs S1Model::carve_denoise(Carver& c, int B, int Ns, int T) con
 void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* tsteps, int t_scalar, bool cond_full,
                            const bf16* goal, const bf16* rgbd, int B, int Ns, int T, int mode, float* x_io,
                            const float* noise, float* eps, const DdpmCoef& cf, cudaStream_t s) const {
-  const int D = dims.D, Mtok = 2 + 16 * dims.frames;
+  const int D = dims.D, Mtok = dims.cond_tokens();
   const long R = (long)B * Ns * T;
   const int ldkv = kv_all_.N;
+  const bool critic = mode == 2;  // stand-alone policy's predict_critic: no causal mask, memory tokens only, critic head
+  const int kv_first = critic ? 1 + dims.goal_slots : 0, kv_len = Mtok - kv_first;
   embed_actions(x_t, in_w_, in_b_, out_pos_, d.x, R, T, s);
   if (cond_full) {
-    build_cond(tsteps, t_scalar, goal, rgbd, cond_pos_, d.cond, B, Mtok, 0, Mtok, s);
+    build_cond(tsteps, t_scalar, goal, rgbd, cond_pos_, d.cond, B, Mtok, 0, Mtok, s, dims.goal_slots);
     linear(kv_all_, d.cond, D, d.ckv, ldkv, B * Mtok, GemmEpilogue(), s);
   } else {
     // only the time token changed: refresh row 0 of every environment (strided A and out)
-    build_cond(tsteps, t_scalar, goal, rgbd, cond_pos_, d.cond, B, Mtok, 0, 1, s);
+    build_cond(tsteps, t_scalar, goal, rgbd, cond_pos_, d.cond, B, Mtok, 0, 1, s, dims.goal_slots);
     linear(kv_all_, d.cond, Mtok * D, d.ckv, Mtok * ldkv, B, GemmEpilogue(), s);
   }
   const float scale48 = 1.0f / sqrtf(48.f);
@@ -470,7 +484,7 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     p.q = d.qkv, p.k = d.qkv + D, p.v = d.qkv + 2 * D, p.o = d.att;
     p.ldq = p.ldk = p.ldv = 3 * D, p.ldo = D;
     p.heads_q = p.heads_kv = dims.heads, p.hd = 48, p.batch = B * Ns, p.seq_q = p.seq_k = T, p.kv_div = 1;
-    p.causal = 1, p.scale = scale48;
+    p.causal = critic ? 0 : 1, p.scale = scale48;
     attention(p, s);
     res_gemm_ln(L.sa_out, d.att, D, &L.n2);
 
@@ -480,6 +494,12 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     pc.ldq = D, pc.ldk = pc.ldv = ldkv, pc.ldo = D;
     pc.heads_q = pc.heads_kv = dims.heads, pc.hd = 48, pc.batch = B * Ns, pc.seq_q = T, pc.seq_k = Mtok;
     pc.kv_div = Ns, pc.scale = scale48;
+    if (kv_first > 0) {
+      // `cond_critic_mask` (navdp_policy.py L131-132): the time / goal slots are invisible -> every environment's keys are
+      // the kv_len memory tokens; var-len addressing skips the masked rows without copying
+      pc.k += (long)kv_first * ldkv, pc.v += (long)kv_first * ldkv;
+      pc.k_len = d.klen, pc.k_slot = Mtok, pc.seq_k = kv_len;   // slotted addressing: env e owns rows [e * Mtok, +kv_len)
+    }
     attention(pc, s);
     const bool ffb = ff_block_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536;
     res_gemm_ln(L.ca_out, d.att, D, ffb ? nullptr : &L.n3);  // the FF-block kernel applies norm3 itself
@@ -498,6 +518,10 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
       res_gemm_ln(L.ff2, d.hid, 4 * D, next_ln);
     }
   }
+  if (critic) {
+    critic_head(xc, final_ln_.w, final_ln_.b, critic_w_, critic_b_, (long)B * Ns, T, eps, s);
+    return;
+  }
   head_ddpm(xc, final_ln_.w, final_ln_.b, head_w_, head_b_, R, mode, x_io, noise, eps, cf, s);
 }
 
@@ -515,6 +539,18 @@ void S1Model::navdp_eps(void* ws, size_t ws_bytes, const float* x_t, const int* 
   Carver c(ws, ws_bytes);
   DenoiseBufs d = carve_denoise(c, B, Ns, T);
   decoder_pass(d, x_t, tsteps, t_scalar, true, goal, rgbd, B, Ns, T, 0, nullptr, nullptr, eps, DdpmCoef(), s);
+}
+
+void S1Model::navdp_critic(void* ws, size_t ws_bytes, const float* traj, const bf16* rgbd, float* critic, int B, int Ns, int T,
+                           cudaStream_t s) const {
+  N1_CHECK(loaded_ && dims.standalone && critic_w_, "navdp_critic: needs the stand-alone NavDP policy weights");
+  N1_CHECK(ws != nullptr && traj && rgbd && critic, "navdp_critic: null buffers");
+  N1_CHECK(T >= 1 && T <= dims.T, "predict horizon exceeds out_pos_embed");
+  Carver c(ws, ws_bytes);
+  DenoiseBufs d = carve_denoise(c, B, Ns, T);
+  fill_int(d.klen, dims.mem_tokens(), B, s);
+  // nogoal embedding = zeros in every time / goal slot (navdp_policy.py L174-181); those slots are masked anyway
+  decoder_pass(d, traj, nullptr, 0, true, nullptr, rgbd, B, Ns, T, 2, nullptr, nullptr, critic, DdpmCoef(), s);
 }
 
 // diffusers 0.33.1 DDPMScheduler(num_train_timesteps=N, beta_schedule="squaredcos_cap_v2", clip_sample=True,

@@ -50,6 +50,15 @@ struct S1Dims {
   int vlm_dim = 3584;   // latent width
   int n_query = 4;      // latent tokens per env
   int ddpm_steps = 20;  // num_train_timesteps
+  // Stand-alone NavDP policy (NavDPNet, internnav/model/basemodel/navdp/navdp_policy.py): RGBDBackbone sees `frames` RGB
+  // frames but ONE depth frame, the condition row is [time, goal, goal, goal, memory tokens], there is no VLM goal path,
+  // and a critic head ranks the sampled trajectories.  Defaults = the InternVLA-N1 head.
+  int frames_depth = 0;  // 0: as many depth frames as RGB frames
+  int goal_slots = 1;    // condition tokens that carry the goal embedding
+  int standalone = 0;    // 1: NavDPNet wiring (no vlm_embed_mlp / goal_compressor, fp32 ImageNet constants, critic head)
+  int depth_frames() const { return frames_depth > 0 ? frames_depth : frames; }
+  int mem_tokens() const { return 16 * frames; }
+  int cond_tokens() const { return 1 + goal_slots + mem_tokens(); }
 };
 
 class S1Model {
@@ -80,6 +89,12 @@ class S1Model {
   void navdp_sample(void* ws, size_t ws_bytes, const bf16* goal, const bf16* rgbd, const float* x_init,
                     const float* step_noise, float* traj_out, int B, int Ns, int T, int K, cudaStream_t s) const;
 
+  // Critic of the stand-alone policy (navdp_policy.py L172-187 `predict_critic`): trajectories fp32 [B*Ns, T, 3], memory
+  // tokens bf16 [B, mem_tokens, D] -> critic fp32 [B*Ns].  Full self-attention, cross-attention restricted to the memory
+  // tokens (the time / goal slots are masked: `cond_critic_mask`), LayerNorm, mean over T, critic_head.
+  void navdp_critic(void* ws, size_t ws_bytes, const float* traj, const bf16* rgbd, float* critic, int B, int Ns, int T,
+                    cudaStream_t s) const;
+
   static void ddpm_tables(int N, std::vector<DdpmCoef>& coef);
 
  private:
@@ -104,7 +119,7 @@ class S1Model {
   Vit load_vit(const WeightSource& ws, bool depth, cudaStream_t s);
   DecLayer load_dec_layer(const WeightSource& ws, bool with_kv, cudaStream_t s);
   size_t vit_forward(const Vit& v, Carver c, const float* img, bool depth, int n_img, bf16* mem, int slot_base,
-                     cudaStream_t s, bool with_pe = true) const;
+                     cudaStream_t s, bool with_pe = true, int frames_per_env = 0) const;
   size_t rgbd_impl(Carver c, const float* rgb, const float* depth, bf16* out, int B, cudaStream_t s) const;
   size_t goal_impl(Carver c, const bf16* latents, bf16* goal, int B, cudaStream_t s) const;
   DenoiseBufs carve_denoise(Carver& c, int B, int Ns, int T) const;
@@ -132,6 +147,7 @@ class S1Model {
   Lin kv_all_;                               // all layers' cross-attention K/V projections stacked: [layers*2D, D]
   LNp final_ln_;
   float *head_w_ = nullptr, *head_b_ = nullptr;
+  float *critic_w_ = nullptr, *critic_b_ = nullptr;  // stand-alone policy only: critic_head [1, D], [1]
 };
 
 }  // namespace n1

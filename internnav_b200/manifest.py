@@ -68,6 +68,48 @@ def navdp_shapes(memory_size=2, predict_size=32, temporal_depth=16, token_dim=38
     return OrderedDict(items)
 
 
+def navdp_policy_shapes(memory_size=8, predict_size=24, temporal_depth=16, token_dim=384):
+    """Inference-relevant tensors of the stand-alone NavDPNet (navdp_policy.py L62-134; the image / pixel goal encoders and
+    auxiliary heads, which only `forward` (training) reads, are left out), under the reference's state_dict names."""
+    D = token_dim
+    items = _vit("rgbd_encoder.rgb_model.") + _vit("rgbd_encoder.depth_model.")
+    items += [("rgbd_encoder.former_query.position_embedding.weight", (memory_size * 16, D)),
+              ("rgbd_encoder.former_pe.position_embedding.weight", ((memory_size + 1) * 256, D))]
+    for i in range(2):
+        items += _dec_layer("rgbd_encoder.former_net.layers.%d." % i, D, 2048)
+    items += [("rgbd_encoder.project_layer.weight", (D, D)), ("rgbd_encoder.project_layer.bias", (D,)),
+              ("point_encoder.weight", (D, 3)), ("point_encoder.bias", (D,))]
+    for i in range(temporal_depth):
+        items += _dec_layer("decoder.layers.%d." % i, D, 4 * D)
+    items += [("input_embed.weight", (D, 3)), ("input_embed.bias", (D,)),
+              ("cond_pos_embed.position_embedding.weight", (memory_size * 16 + 4, D)),
+              ("out_pos_embed.position_embedding.weight", (predict_size, D)),
+              ("layernorm.weight", (D,)), ("layernorm.bias", (D,)), ("action_head.weight", (3, D)), ("action_head.bias", (3,)),
+              ("critic_head.weight", (1, D)), ("critic_head.bias", (1,))]
+    return OrderedDict(items)
+
+
+def random_navdp_policy_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
+    """Seeded random weights of the stand-alone NavDPNet shapes (same scaling rules as random_navdp_state_dict)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = OrderedDict()
+    for name, shape in navdp_policy_shapes(**dims).items():
+        last = name.split(".")[-1]
+        if (("norm" in name and last == "weight") or last == "gamma") and len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif "position_embedding" in name or "pos_embed" in name or "cls_token" in name or "mask_token" in name:
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) / fan_in ** 0.5
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        out[name] = t.to(device=device, dtype=dtype)
+    return out
+
+
 def random_navdp_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
     """Random weights of the right shapes (synthetic benchmark / smoke runs; there are no checkpoints offline).
     Scales keep activations O(1); tables the reference zero-initialises get small non-zero values."""

@@ -101,7 +101,16 @@ class S1TrainStep:
         self._touched = set()   # tensors that received a gradient in the current step (torch.optim skips the others)
 
     def refresh(self):
-        self.w = {k: self.ops.cast(v) for k, v in self.p32.items() if v.is_floating_point()}
+        """Working copies in the kernel dtype, refreshed IN PLACE after the first call: a captured CUDA graph of the step
+        (DualSystemTrainer(graph_s1=True)) keeps reading the same buffers."""
+        for k, v in self.p32.items():
+            if not v.is_floating_point():
+                continue
+            cur = self.w.get(k)
+            if cur is not None and cur.shape == v.shape and cur.device == v.device:
+                cur.copy_(v)
+            else:
+                self.w[k] = self.ops.cast(v)
 
     # ---- primitives on the backend ----------------------------------------------------------------------------
     def _f32(self, name):
@@ -194,13 +203,14 @@ class S1TrainStep:
 
     # ---- DINOv2 ViT-S (depth branch; dinov2.py L180-322) ------------------------------------------------------
     def _R(self, src_side, dst_side, device):
-        key = (src_side, dst_side)
+        key = (src_side, dst_side, str(device))     # cached ON the device: a host copy could not be read under graph capture
         if key not in self._resample:
             n = src_side * src_side
             eye = torch.eye(n).reshape(n, 1, src_side, src_side)
             s = float(dst_side + 0.1) / src_side
-            self._resample[key] = F.interpolate(eye, scale_factor=(s, s), mode="bicubic", antialias=False).reshape(n, -1).t().contiguous()
-        return self._resample[key].to(device)
+            r = F.interpolate(eye, scale_factor=(s, s), mode="bicubic", antialias=False).reshape(n, -1).t().contiguous()
+            self._resample[key] = r.to(device)
+        return self._resample[key]
 
     def vit_fwd(self, p, frames):
         """frames: [n, 224, 224] fp32 depth frames.  The reference feeds the ViT three identical channels
@@ -446,7 +456,11 @@ class S1TrainStep:
         dev = self.w["layernorm.weight"].device
         Bb, f = traj_depths.shape[:2]
         hs = traj_hidden_states.to(dev).unsqueeze(1).repeat(1, f, 1, 1).flatten(0, 1)
-        mask = (torch.arange(f).expand(Bb, f) < video_frame_num.cpu().unsqueeze(1)).flatten(0, 1)[:, None, None].float().to(dev)
+        if video_frame_num.device.type == "cuda":   # device-resident counts: no host round trip (CUDA-graph capturable)
+            mask = (torch.arange(f, device=dev).expand(Bb, f) < video_frame_num.to(dev).unsqueeze(1))
+            mask = mask.flatten(0, 1)[:, None, None].float()
+        else:
+            mask = (torch.arange(f).expand(Bb, f) < video_frame_num.cpu().unsqueeze(1)).flatten(0, 1)[:, None, None].float().to(dev)
         cur_d = traj_depths.to(dev).flatten(0, 1)
         g_d = traj_depths.to(dev)[:, 0:1].repeat(1, f, 1, 1).flatten(0, 1)
         depths_dp = torch.stack([g_d, cur_d], dim=1).unsqueeze(-1)

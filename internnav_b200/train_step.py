@@ -45,7 +45,8 @@ def warmup_cosine(base_lr, total_steps, warmup_ratio=0.03, min_ratio=0.0):
 
 class DualSystemTrainer:
     def __init__(self, model, navdp_state_dict, latent_queries, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 bucket_cap_mb=100, process_group=None, max_grad_norm=None, lr_schedule=None, accumulation_steps=1):
+                 bucket_cap_mb=100, process_group=None, max_grad_norm=None, lr_schedule=None, accumulation_steps=1,
+                 graph_s1=False):
         """model: internnav_b200.internvla_n1.InternVLAN1ForCausalLM with weights loaded (the frozen parts are used from
         it); navdp_state_dict: {reference name: tensor} for `model.navdp.*`; latent_queries [1, n_query, H]."""
         self.model = model
@@ -68,6 +69,11 @@ class DualSystemTrainer:
         self.m = {k: torch.zeros_like(g) for k, g in self.buckets.grads.items()}
         self.v = {k: torch.zeros_like(g) for k, g in self.buckets.grads.items()}
         self.steps, self._micro, self._touched = 0, 0, set()
+        self.profile_phases = False
+        # graph_s1: replay the System-1 forward / backward (several thousand kernel launches driven from Python, one ctypes
+        # call each: the step is host-bound without it, profiles/README.md) from a CUDA graph captured on the first step of
+        # a given batch shape
+        self.graph_s1, self._s1_graphs = bool(graph_s1), {}
         self._s1_views = OrderedDict((k, g) for k, g in self.buckets.grads.items() if k != "model.latent_queries")
         self.timing = {}
         import ctypes
@@ -100,6 +106,47 @@ class DualSystemTrainer:
         return self.s1.forward_backward(hs, rgb_tokens, td, batch["traj_poses"], batch["video_frame_num"], noise,
                                         timesteps, self.alphas_cumprod, rgb_has_pe=False, grads_into=grads_into)
 
+    def _s1_graphed(self, batch, hs, noise, timesteps):
+        """System-1 forward / backward through a captured CUDA graph: static input buffers, gradients accumulate into the
+        bucket views exactly as in the eager path.  -> (loss, set of touched names, d loss / d TRAJ states)."""
+        dev = self.device
+        ti, td = batch["traj_images"].to(dev), batch["traj_depths"].to(dev)
+        key = (tuple(ti.shape), tuple(hs.shape), tuple(noise.shape))
+        ent = self._s1_graphs.get(key)
+        src = dict(ti=ti, td=td.float(), poses=batch["traj_poses"].to(dev).float(), vfn=batch["video_frame_num"].to(dev),
+                   noise=noise.to(dev).float(), ts=timesteps.to(dev), hs=hs)
+        if ent is None:
+            st = {k: v.clone() for k, v in src.items()}
+
+            def run():
+                f = st["ti"].shape[1]
+                goal_i = st["ti"][:, 0:1].repeat(1, f, 1, 1, 1).flatten(0, 1)
+                images_dp = torch.stack([goal_i, st["ti"].flatten(0, 1)], dim=1)
+                rgb_tokens = self.model.model.navdp.rgb_memory_tokens(images_dp)
+                return self.s1.forward_backward(st["hs"], rgb_tokens, st["td"], st["poses"], st["vfn"], st["noise"], st["ts"],
+                                                self.alphas_cumprod, rgb_has_pe=False, grads_into=self._s1_views)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                run()                         # warm-up on the capture stream: scratch buffers, cached tables
+                side.synchronize()
+                self.buckets.zero()           # the warm-up accumulated into the views
+                before = _lib.prof_read()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    loss, grads, dhs = run()
+                nodes = _lib.prof_read()      # kernels captured into the graph = launches of every replay
+                _lib.lib().n1_prof_add(before["gemm_launches"], before["total_launches"])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            ent = self._s1_graphs[key] = (g, st, loss, set(grads), dhs, nodes)
+        g, st, loss, touched, dhs, nodes = ent
+        for k, v in src.items():
+            st[k].copy_(v, non_blocking=True)
+        g.replay()
+        _lib.lib().n1_prof_add(nodes["gemm_launches"], nodes["total_launches"])
+        return loss, touched, dhs
+
     def loss_and_grads(self, batch, noise, timesteps):
         """Parity entry point: (loss, {name: fp32 gradient}, TRAJ states) for one batch; no exchange, no update.
         batch: the collated dict of internnav_b200.training.collate_traj_batch (tensors may live on the host)."""
@@ -119,8 +166,18 @@ class DualSystemTrainer:
         self._micro += 1
         last = self._micro >= self.accumulation_steps
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if dist_on else None
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.profile_phases else None
+        if pe:
+            pe[0].record()
         hs = self._s2_forward(batch)
-        loss, grads, dhs = self._s1_forward_backward(batch, hs, noise, timesteps, grads_into=self._s1_views)
+        if pe:
+            pe[1].record()
+        if self.graph_s1:
+            loss, grads, dhs = self._s1_graphed(batch, hs, noise, timesteps)
+        else:
+            loss, grads, dhs = self._s1_forward_backward(batch, hs, noise, timesteps, grads_into=self._s1_views)
+        if pe:
+            pe[2].record()
         self._touched.update(grads)
         lat_view = self.buckets.grads["model.latent_queries"]
         lat_bucket = self.buckets.bucket_of("model.latent_queries")
@@ -133,6 +190,8 @@ class DualSystemTrainer:
             ev[1].record()
         lat_view += self.model._s2.train_backward(dhs).reshape(self.latent.shape)
         self._touched.add("model.latent_queries")
+        if pe:
+            pe[3].record()
         if not last:
             return loss
         if dist_on:
@@ -163,7 +222,19 @@ class DualSystemTrainer:
                        eps=o["eps"], weight_decay=o["weight_decay"], step=self.steps)
         self.s1.refresh()
         self.model._s2.set_latent_queries(self.latent)
+        if pe:
+            pe[4].record()
+            self._phase_events = pe
         return loss
+
+    def phase_ms(self):
+        """Device time of the phases of the last step run with `profile_phases = True` (CUDA events; synchronises)."""
+        pe = getattr(self, "_phase_events", None)
+        if pe is None:
+            return None
+        pe[4].synchronize()
+        return {"s2_forward": pe[0].elapsed_time(pe[1]), "s1_forward_backward": pe[1].elapsed_time(pe[2]),
+                "s2_backward": pe[2].elapsed_time(pe[3]), "exchange_clip_adamw_refresh": pe[3].elapsed_time(pe[4])}
 
     def exchange_ms(self):
         """CUDA-event times of the last exchanged step: (launch window of the overlapped buckets, exposed tail = from the

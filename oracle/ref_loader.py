@@ -89,6 +89,52 @@ def build_reference_navdp(predict_size=32, memory_size=2, navdp_version=0.1):
     return m.eval()
 
 
+def build_reference_navdp_policy(memory_size=8, predict_size=24):
+    """Construct the reference's stand-alone NavDPNet (internnav/model/basemodel/navdp/navdp_policy.py) in fp32 on the CPU.
+    Shims: bare `internnav.configs.*` modules holding two attribute-bag config classes (the real ones are pydantic models the
+    policy only reads attributes from), `torch.load` -> {} for the DepthAnything checkpoint, and `torch.device` -> cpu
+    while the constructor runs (it hard-codes cuda:<local_rank>)."""
+    import torch
+
+    load_reference_navdp()
+    for name in ("internnav.configs", "internnav.configs.model", "internnav.configs.model.base_encoders",
+                 "internnav.configs.trainer", "internnav.configs.trainer.exp"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+
+    class _Bag:
+        def __init__(self, **k):
+            self.__dict__.update(k)
+
+    sys.modules["internnav.configs.model.base_encoders"].ModelCfg = _Bag
+    sys.modules["internnav.configs.trainer.exp"].ExpCfg = _Bag
+    if "internnav.model.basemodel.navdp" not in sys.modules:
+        _bare_package("internnav.model.basemodel.navdp", os.path.join(REF, "internnav", "model", "basemodel", "navdp"))
+    real_load, real_dev = torch.load, torch.device
+
+    class _CpuDevice:
+        def __new__(cls, *a, **k):
+            return real_dev("cpu")
+
+    torch.load = lambda *a, **k: {}
+    try:
+        mod = importlib.import_module("internnav.model.basemodel.navdp.navdp_policy")
+        il = dict(image_size=224, memory_size=memory_size, predict_size=predict_size, pixel_channel=4, temporal_depth=16,
+                  heads=8, channels=3, dropout=0.1, token_dim=384, scratch=False, finetune=False)
+        cfg = mod.NavDPModelConfig(model_cfg={"model": {}, "il": il, "local_rank": 0})
+        torch.device = _CpuDevice
+        try:
+            net = mod.NavDPNet(cfg)
+        finally:
+            torch.device = real_dev
+    finally:
+        torch.load = real_load
+    net._device = real_dev("cpu")
+    return net.eval()
+
+
 def load_reference_vln_utils():
     import importlib.util
 

@@ -224,3 +224,17 @@ def test_dual_system_training_step_vs_oracle():
     before = {k: v.clone() for k, v in list(tr.masters.items())[:5]}
     tr.step(batch, noise, ts)
     assert tr.steps == 1 and any(not torch.equal(before[k], tr.masters[k]) for k in before if k in tr.buckets.grads)
+    # the CUDA-graph replay of the System-1 forward / backward computes the same step: two trainers from identical state,
+    # one eager and one graphed, two steps each -> identical loss and masters (bit for bit: same kernels, same order)
+    ta = DualSystemTrainer(model, s1_sd, s2_sd["model.latent_queries"], lr=1e-3, max_grad_norm=1.0)
+    tb = DualSystemTrainer(model, s1_sd, s2_sd["model.latent_queries"], lr=1e-3, max_grad_norm=1.0, graph_s1=True)
+    dev_batch = {k: (v.cuda() if torch.is_tensor(v) and k in ("traj_images", "traj_depths", "traj_poses", "video_frame_num")
+                     else v) for k, v in batch.items()}
+    for _ in range(2):
+        la = float(ta.step(dev_batch, noise.cuda(), ts.cuda()))
+        model._s2.set_latent_queries(tb.latent)      # both trainers drive the same System-2 handle
+        lb = float(tb.step(dev_batch, noise.cuda(), ts.cuda()))
+        model._s2.set_latent_queries(ta.latent)
+        assert abs(la - lb) <= 1e-6 * max(1.0, abs(la)), (la, lb)
+    worst = max(float((ta.masters[k] - tb.masters[k]).abs().max()) for k in ta.masters)
+    assert worst < 1e-6, worst
