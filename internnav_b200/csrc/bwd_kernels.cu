@@ -431,6 +431,10 @@ void sgemm_small(const float* A, int lda, int trans_a, const float* B, int ldb, 
 
 void attention_bwd(const AttnBwdParams& p, cudaStream_t s) {
   const AttnParams& f = p.f;
+  if (attention_bwd_mma_supported(p)) {
+    attention_bwd_mma(p, s);
+    return;
+  }
   N1_CHECK(f.batch > 0 && f.heads_kv > 0 && f.heads_q % f.heads_kv == 0 && f.kv_div >= 1, "attention_bwd: bad head counts");
   N1_CHECK(f.hd <= 128 && p.dq && p.dk && p.dv && p.dout && f.o, "attention_bwd: null buffers / head_dim > 128");
   N1_CHECK(f.batch % f.kv_div == 0, "attention_bwd: batch must be a multiple of kv_div");

@@ -57,6 +57,10 @@ struct AttnBwdParams {
   float* dv;             // [rows_k, heads_kv * hd]
 };
 void attention_bwd(const AttnBwdParams& p, cudaStream_t s);
+// tensor-core path (attention_bwd_mma.cu): fixed-length MHA, head_dim 48 / 64, one head's operands within shared memory;
+// attention_bwd() takes it whenever it applies (N1_ATTN_BWD_MMA=0 keeps the scalar kernel)
+bool attention_bwd_mma_supported(const AttnBwdParams& p);
+void attention_bwd_mma(const AttnBwdParams& p, cudaStream_t s);
 
 // Fused AdamW step on fp32 master parameters with a bf16 working copy (torch.optim.AdamW semantics: decoupled decay,
 // bias correction): p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p)

@@ -94,8 +94,11 @@ def test_rope_transposed_is_the_adjoint():
 
 @pytest.mark.parametrize("B,Sq,Sk,Hq,Hkv,hd,causal", [(6, 32, 32, 8, 8, 48, True), (6, 32, 34, 8, 8, 48, False),
                                                       (3, 257, 257, 6, 6, 64, False), (2, 32, 1024, 8, 8, 48, False),
-                                                      (2, 4, 300, 28, 4, 128, True), (1, 1, 4, 8, 8, 48, False)])
+                                                      (2, 4, 300, 28, 4, 128, True), (1, 1, 4, 8, 8, 48, False),
+                                                      (2, 40, 72, 6, 6, 64, True), (5, 100, 100, 6, 6, 64, True)])
 def test_attention_bwd(B, Sq, Sk, Hq, Hkv, hd, causal):
+    """Fixed-length MHA with head_dim 48 / 64 whose four operand tiles fit the shared memory of an SM runs the tensor-core
+    kernel (attention_bwd_mma.cu); GQA, head_dim 128 and the 1024-key case run the scalar kernel (bwd_kernels.cu)."""
     from internnav_b200 import _bwd as K, _lib as L
     torch.manual_seed(B * Sq + Sk)
     q = torch.randn(B * Sq, Hq * hd, device="cuda").bfloat16()
@@ -230,6 +233,7 @@ def test_dual_system_training_step_vs_oracle():
     tb = DualSystemTrainer(model, s1_sd, s2_sd["model.latent_queries"], lr=1e-3, max_grad_norm=1.0, graph_s1=True)
     dev_batch = {k: (v.cuda() if torch.is_tensor(v) and k in ("traj_images", "traj_depths", "traj_poses", "video_frame_num")
                      else v) for k, v in batch.items()}
+    model._s2.set_latent_queries(ta.latent)          # `tr.step` above left ITS updated queries in the shared handle
     for _ in range(2):
         la = float(ta.step(dev_batch, noise.cuda(), ts.cuda()))
         model._s2.set_latent_queries(tb.latent)      # both trainers drive the same System-2 handle
