@@ -133,6 +133,86 @@ def random_navdp_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- NextDiT System 1 (f1)
+def _enc_layer(p, D, ff):
+    out = _mha(p + "self_attn.", D)
+    out += [(p + "linear1.weight", (ff, D)), (p + "linear1.bias", (ff,)), (p + "linear2.weight", (D, ff)),
+            (p + "linear2.bias", (D,))]
+    for n in ("norm1", "norm2"):
+        out += [(p + n + ".weight", (D,)), (p + n + ".bias", (D,))]
+    return out
+
+
+def nextdit_shapes(dim=384, layers=12, heads=6, latent=768, vlm_token_dim=3584, ffn=1024):
+    """Tensors of the `nextdit_async` System 1 under the reference's attribute paths below `InternVLAN1ForCausalLM.model`
+    (internvla_n1_arch.py L131-145: cond_projector, rgb_model, memory_encoder, rgb_resampler, action_encoder / decoder,
+    traj_dit = NextDiTCrossAttn(latent_embedding_size=768), nextdit_crossattn_traj.py L46-82)."""
+    D, L = dim, latent
+    items = [("cond_projector.0.weight", (L, vlm_token_dim)), ("cond_projector.0.bias", (L,)),
+             ("cond_projector.2.weight", (L, L)), ("cond_projector.2.bias", (L,))]
+    items += _vit("rgb_model.")
+    items += [("memory_encoder.memory_pos", (512, D))]
+    for i in range(3):
+        items += _enc_layer("memory_encoder.encoder.layers.%d." % i, D, 2048)
+    items += [("rgb_resampler.query_tokens", (32, L)), ("rgb_resampler.query_pos", (32, L))]
+    for i in range(3):
+        items += _dec_layer("rgb_resampler.decoder.layers.%d." % i, L, 2048)
+    items += [("rgb_resampler.visual_proj.weight", (L, L)), ("rgb_resampler.visual_proj.bias", (L,)),
+              ("action_encoder.weight", (D, 3)), ("action_encoder.bias", (D,)),
+              ("action_decoder.weight", (3, D)), ("action_decoder.bias", (3,))]
+    p = "traj_dit.model."
+    items += [(p + "caption_projection.linear_1.weight", (D, L)), (p + "caption_projection.linear_1.bias", (D,)),
+              (p + "caption_projection.linear_2.weight", (D, D)), (p + "caption_projection.linear_2.bias", (D,)),
+              (p + "patch_embedder.proj.weight", (D, D)), (p + "patch_embedder.proj.bias", (D,)),
+              (p + "time_caption_embed.timestep_embedder.linear_1.weight", (D, 256)),
+              (p + "time_caption_embed.timestep_embedder.linear_1.bias", (D,)),
+              (p + "time_caption_embed.timestep_embedder.linear_2.weight", (D, D)),
+              (p + "time_caption_embed.timestep_embedder.linear_2.bias", (D,)),
+              (p + "time_caption_embed.caption_embedder.0.weight", (D,)), (p + "time_caption_embed.caption_embedder.0.bias", (D,)),
+              (p + "time_caption_embed.caption_embedder.1.weight", (D, D)), (p + "time_caption_embed.caption_embedder.1.bias", (D,))]
+    for i in range(layers):
+        b = "%slayers.%d." % (p, i)
+        items += [(b + "gate", (heads,))]
+        for a in ("attn1.", "attn2."):
+            items += [(b + a + "to_q.weight", (D, D)), (b + a + "to_k.weight", (D, D)), (b + a + "to_v.weight", (D, D)),
+                      (b + a + "norm_q.weight", (D,)), (b + a + "norm_q.bias", (D,)), (b + a + "norm_k.weight", (D,)),
+                      (b + a + "norm_k.bias", (D,))]
+        items += [(b + "attn2.to_out.0.weight", (D, D)), (b + "feed_forward.linear_1.weight", (ffn, D)),
+                  (b + "feed_forward.linear_2.weight", (D, ffn)), (b + "feed_forward.linear_3.weight", (ffn, D)),
+                  (b + "norm1.linear.weight", (4 * D, D)), (b + "norm1.linear.bias", (4 * D,)), (b + "norm1.norm.weight", (D,)),
+                  (b + "ffn_norm1.weight", (D,)), (b + "norm2.weight", (D,)), (b + "ffn_norm2.weight", (D,)),
+                  (b + "norm1_context.weight", (D,))]
+    items += [(p + "norm_out.linear_1.weight", (D, D)), (p + "norm_out.linear_1.bias", (D,)),
+              (p + "norm_out.linear_2.weight", (D, D)), (p + "norm_out.linear_2.bias", (D,))]
+    return OrderedDict(items)
+
+
+def random_nextdit_state_dict(seed=0, device="cpu", dtype=torch.float32, **dims):
+    """Seeded random weights of the NextDiT System-1 shapes.  The reference zero-initialises `gate` (tanh(0) = 0 would
+    switch the cross-attention off): it gets O(0.5) values here so that branch is exercised."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = OrderedDict()
+    for name, shape in nextdit_shapes(**dims).items():
+        last = name.split(".")[-1]
+        if last == "gate":
+            t = 0.5 * torch.randn(shape, generator=g)
+        elif len(shape) == 1 and last in ("weight", "gamma") and ("norm" in name or "caption_embedder.0" in name or last == "gamma"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif "pos_embed" in name or "cls_token" in name or "mask_token" in name:
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif last in ("memory_pos", "query_tokens", "query_pos"):
+            t = 0.5 * torch.randn(shape, generator=g)
+        elif len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) / fan_in ** 0.5
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        out[name] = t.to(device=device, dtype=dtype)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- System 2
 def s2_shapes(cfg, lm_head=False):
     """Qwen2.5-VL parameter names/shapes in the transformers==4.51 checkpoint layout the reference loads, plus

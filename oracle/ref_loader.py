@@ -89,6 +89,17 @@ def build_reference_navdp(predict_size=32, memory_size=2, navdp_version=0.1):
     return m.eval()
 
 
+def load_reference_nextdit():
+    """-> (nextdit_traj, nextdit_crossattn_traj): the reference's own DiT classes, importable here only with stand-ins for
+    the absent `diffusers` leaf modules (oracle/diffusers_standin.py) -- pins the block / model WIRING, not the leaves."""
+    load_reference_navdp()       # registers the bare internnav packages (and the DDPM stand-in)
+    from . import diffusers_standin
+    diffusers_standin.install()
+    a = importlib.import_module("internnav.model.basemodel.internvla_n1.nextdit_traj")
+    b = importlib.import_module("internnav.model.basemodel.internvla_n1.nextdit_crossattn_traj")
+    return a, b
+
+
 def build_reference_navdp_policy(memory_size=8, predict_size=24):
     """Construct the reference's stand-alone NavDPNet (internnav/model/basemodel/navdp/navdp_policy.py) in fp32 on the CPU.
     Shims: bare `internnav.configs.*` modules holding two attribute-bag config classes (the real ones are pydantic models the
