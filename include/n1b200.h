@@ -317,13 +317,27 @@ int n1_op_ff_block(const void* x_bf16, int ldx, const float* ln_w, const float* 
                    const float* b1, const void* w2_bf16, const float* b2, void* out_bf16, int ldo, int M, int cluster,
                    void* stream);
 /* weight-streaming GEMM for M <= 64 rows (decode passes): out bf16 [M, N or N/2 for SwiGLU]; bias fp32 [N] / residual
- * bf16 [M, ldr] may be NULL; act: 0 none, 1 GELU, 2 ReLU, 3 SwiGLU; ws: n1_op_gemm_skinny_workspace_bytes() of scratch */
+ * bf16 [M, ldr] may be NULL; act: 0 none, 1 GELU, 2 ReLU, 3 SwiGLU (tcgen05 GEMM only: 4 tanh-GELU, 5 SiLU); ws: n1_op_gemm_skinny_workspace_bytes() of scratch */
 size_t n1_op_gemm_skinny_workspace_bytes(void);
 int n1_op_gemm_skinny(const void* a_bf16, int lda, const void* w_bf16, int ldw, void* out_bf16, int ldo, int M, int N,
                       int K, const void* bias_f32, const void* residual_bf16, int ldr, int act, void* ws, size_t ws_bytes,
                       void* stream);
 int n1_op_layernorm(const void* x_bf16, int ldx, void* y_bf16, int ldy, const float* w, const float* b, int rows, int D,
                     float eps, int rms, void* stream);
+/* Row kernels of the NextDiT System 1 (reference: nextdit_traj.py L125-178 LuminaNextDiTBlock.forward, L352-356;
+ * internvla_n1.py L399-427).  `mod`: one bf16 vector per group of rows_per_group consecutive rows (stride ld_mod) or NULL.
+ *   mode 0: out = RMSNorm(x) * w * (1 + mod[g]);  1: out = LayerNorm_noaffine(x) * (1 + mod[g]);
+ *   mode 2: out = res + tanh(mod[g]) * RMSNorm(x) * w.     D % 8 == 0, D <= 1024; w fp32 [D] or NULL. */
+int n1_op_mod_norm(const void* x_bf16, int ldx, const float* w, const void* mod_bf16, int ld_mod, int rows_per_group,
+                   const void* res_bf16, int ldr, void* out_bf16, int ldo, int64_t rows, int D, float eps, int mode,
+                   void* stream);
+int n1_op_add(const void* a_bf16, const void* b_bf16, void* out_bf16, int64_t n, void* stream);
+/* action_encoder (nn.Linear(3, D)) + sinusoidal step code: lat fp32 [rows, 3] -> bf16 [rows, D]; w [D, 3], b [D], pos [T, D] */
+int n1_op_action_embed(const float* lat, const float* w, const float* b, const float* pos, void* out_bf16, int64_t rows,
+                       int T, int D, void* stream);
+/* classifier-free guidance + FlowMatchEulerDiscreteScheduler.step: pred bf16 [(cfg ? 2 : 1) * n, ld] (columns 0..2),
+ * lat fp32 [n, 3] updated in place (values kept bf16-representable, as the reference keeps the latents in the model dtype) */
+int n1_op_cfg_euler(const void* pred_bf16, int ld, int64_t n, int cfg, float scale, float dt, float* lat, void* stream);
 /* q/k/v/o bf16 with row strides ld*; sequences fixed-length (cu_* NULL) or varlen (int32 prefix sums on device) */
 int n1_op_attention(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo, int heads_q,
                     int heads_kv, int head_dim, int batch, int seq_q, int seq_k, const int32_t* cu_q,

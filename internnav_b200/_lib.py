@@ -75,6 +75,11 @@ SYMBOLS = {
                                   c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
                                 c_void_p]),
+    "n1_op_mod_norm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                               ctypes.c_int64, c_int, c_float, c_int, c_void_p]),
+    "n1_op_add": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p]),
+    "n1_op_action_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_int, c_void_p]),
+    "n1_op_cfg_euler": (c_int, [c_void_p, c_int, ctypes.c_int64, c_int, c_float, c_float, c_void_p, c_void_p]),
     "n1_op_attention_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_int, ctypes.c_int64, c_int, c_float, ctypes.POINTER(c_int), c_void_p]),
     "n1_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -82,7 +87,7 @@ SYMBOLS = {
 }
 
 OP_RGBD, OP_GOAL, OP_DENOISE = 1, 2, 3
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_SWIGLU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SWIGLU, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3, 4, 5
 
 
 def lib():
@@ -184,12 +189,60 @@ def gemm_skinny(a, w, bias=None, residual=None, act=ACT_NONE, ws=None):
     return out
 
 
-def layernorm(x, w, b=None, eps=1e-5, rms=False):
+def layernorm(x, w, b=None, eps=1e-5, rms=False, out=None):
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
-    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    check(lib().n1_op_layernorm(c_void_p(x.data_ptr()), x.stride(0), ptr(y), y.stride(0), ptr(w), ptr(b), x.shape[0],
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else out
+    assert y.stride(1) == 1 and y.shape == x.shape
+    check(lib().n1_op_layernorm(c_void_p(x.data_ptr()), x.stride(0), c_void_p(y.data_ptr()), y.stride(0), ptr(w), ptr(b), x.shape[0],
                                 x.shape[1], eps, 1 if rms else 0, stream_ptr()))
     return y
+
+
+MOD_RMS_SCALE, MOD_LN_SCALE, MOD_GATED_RESIDUAL = 0, 1, 2
+
+
+def mod_norm(x, w, mod, rows_per_group, eps, mode, residual=None, out=None):
+    """Modulated / gated norms of the NextDiT block (csrc/nextdit_kernels.cu).  x bf16 [rows, D] (row stride allowed),
+    w fp32 [D] or None, mod bf16 [groups, D] view (row stride allowed) or None."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    if mod is not None:
+        assert mod.dtype == torch.bfloat16 and mod.stride(1) == 1 and mod.shape[1] == x.shape[1]
+        assert mod.shape[0] * rows_per_group == x.shape[0]
+    check(lib().n1_op_mod_norm(c_void_p(x.data_ptr()), x.stride(0), ptr(w), c_void_p(mod.data_ptr()) if mod is not None else None,
+                               mod.stride(0) if mod is not None else 0, int(rows_per_group),
+                               c_void_p(residual.data_ptr()) if residual is not None else None,
+                               residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()), out.stride(0),
+                               x.shape[0], x.shape[1], float(eps), int(mode), stream_ptr()))
+    return out
+
+
+def add(a, b, out=None):
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().n1_op_add(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
+    return out
+
+
+def action_embed(lat, w, b, pos, out=None):
+    """lat fp32 [rows, 3], w fp32 [D, 3], b fp32 [D], pos fp32 [T, D] -> bf16 [rows, D]."""
+    assert lat.dtype == torch.float32 and lat.is_contiguous() and lat.shape[-1] == 3
+    rows, (T, D) = lat.numel() // 3, pos.shape
+    if out is None:
+        out = torch.empty(rows, D, device=lat.device, dtype=torch.bfloat16)
+    check(lib().n1_op_action_embed(ptr(lat), ptr(w), ptr(b), ptr(pos), ptr(out), rows, T, D, stream_ptr()))
+    return out
+
+
+def cfg_euler(pred, n, cfg, scale, dt, lat):
+    """lat fp32 [n, 3] <- bf16(lat + dt * guided(pred)); pred bf16 [(2 if cfg else 1) * n, >= 3]."""
+    assert pred.dtype == torch.bfloat16 and pred.stride(1) == 1 and lat.dtype == torch.float32 and lat.is_contiguous()
+    assert pred.shape[0] == (2 if cfg else 1) * n and lat.numel() == 3 * n
+    check(lib().n1_op_cfg_euler(c_void_p(pred.data_ptr()), pred.stride(0), n, 1 if cfg else 0, float(scale), float(dt), ptr(lat),
+                                stream_ptr()))
+    return lat
 
 
 def attention(q, k, v, heads_q, heads_kv, head_dim, batch, seq_q, seq_k, cu_q=None, cu_k=None, max_seq_q=0, kv_div=1,

@@ -615,6 +615,22 @@ int n1_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, void* out,
     gemm_skinny(B16(a), lda, B16(w), ldw, B16(out), ldo, M, N, K, e, static_cast<float*>(ws), S(stream));
   });
 }
+int n1_op_mod_norm(const void* x, int ldx, const float* w, const void* mod, int ld_mod, int rows_per_group, const void* res,
+                   int ldr, void* out, int ldo, int64_t rows, int D, float eps, int mode, void* stream) {
+  return guard([&] {
+    mod_norm(B16(x), ldx, w, B16(mod), ld_mod, rows_per_group, B16(res), ldr, B16(out), ldo, rows, D, eps, mode, S(stream));
+  });
+}
+int n1_op_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  return guard([&] { add_bf16(B16(a), B16(b), B16(out), n, S(stream)); });
+}
+int n1_op_action_embed(const float* lat, const float* w, const float* b, const float* pos, void* out, int64_t rows, int T, int D,
+                       void* stream) {
+  return guard([&] { action_embed(lat, w, b, pos, B16(out), rows, T, D, S(stream)); });
+}
+int n1_op_cfg_euler(const void* pred, int ld, int64_t n, int cfg, float scale, float dt, float* lat, void* stream) {
+  return guard([&] { cfg_euler(B16(pred), ld, n, cfg, scale, dt, lat, S(stream)); });
+}
 int n1_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* w, const float* b, int rows, int D, float eps,
                     int rms, void* stream) {
   return guard([&] { layernorm(B16(x), ldx, B16(y), ldy, w, b, rows, D, eps, rms, S(stream)); });

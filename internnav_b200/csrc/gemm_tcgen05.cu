@@ -311,6 +311,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else if (args.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (args.act == ACT_GELU_TANH) {  // nn.GELU(approximate="tanh"): the NextDiT condition projections
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + tanhf(0.7978845608028654f * (v[j] + 0.044715f * v[j] * v[j] * v[j])));
+        } else if (args.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
         }
         if (args.gamma) {
 #pragma unroll

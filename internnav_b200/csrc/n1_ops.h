@@ -34,7 +34,7 @@ struct Error : std::runtime_error {
 // ------------------------------------------------------------------------------------------- GEMM
 // out[M, N'] = epilogue(A[M,K] @ W[N,K]^T).  A and W are bf16, K-major (row-major with leading
 // dimensions lda / ldw in elements, multiples of 8).  Accumulation in fp32 (TMEM).
-enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3, ACT_GELU_TANH = 4, ACT_SILU = 5 };
 
 struct GemmEpilogue {
   const float* bias = nullptr;      // [N]
@@ -125,6 +125,20 @@ void attention_tc128(const AttnParams& p, cudaStream_t stream);
 // residual stream held in tensor memory.  x / out bf16 [M, ld] (may alias), w1 [1536, 384], w2 [384, 1536] contiguous.
 void ff_block_384(const bf16* x, int ldx, const float* ln_w, const float* ln_b, float eps, const bf16* w1, const float* b1,
                   const bf16* w2, const float* b2, bf16* out, int ldo, int M, int cluster, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------- NextDiT rows (nextdit_kernels.cu)
+// Modulated / gated norms of LuminaNextDiTBlock (nextdit_traj.py L125-178) over bf16 rows of width D <= 1024, D % 8 == 0;
+// `mod` holds one vector per group of `rows_per_group` consecutive rows (row stride ld_mod), or is null:
+//   mode 0: out = RMSNorm(x) * w * (1 + mod[g])     mode 1: out = LayerNorm_noaffine(x) * (1 + mod[g])
+//   mode 2: out = res + tanh(mod[g]) * RMSNorm(x) * w
+void mod_norm(const bf16* x, int ldx, const float* w, const bf16* mod, int ld_mod, int rows_per_group, const bf16* res, int ldr,
+              bf16* out, int ldo, long rows, int D, float eps, int mode, cudaStream_t stream);
+void add_bf16(const bf16* a, const bf16* b, bf16* out, long n, cudaStream_t stream);
+// action_encoder + positional code (internvla_n1.py L401-409): lat fp32 [rows, 3] -> bf16 [rows, D]; pos fp32 [T, D]
+void action_embed(const float* lat, const float* w, const float* b, const float* pos, bf16* out, long rows, int T, int D,
+                  cudaStream_t stream);
+// classifier-free guidance + flow-matching Euler update (internvla_n1.py L422-427): pred bf16 [2n or n, ld], lat fp32 [n, 3]
+void cfg_euler(const bf16* pred, int ld, long n, int cfg, float scale, float dt, float* lat, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------- action tail (postprocess.cu)
 // traj fp32 [B * Ns, T, 3] (sampler output, un-normalised) -> ids int32 [B, cap] (zero padded), count int32 [B] (ids the

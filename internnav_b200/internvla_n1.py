@@ -10,9 +10,10 @@ tensors.  Everything is batched over B independent environments, each treated ex
 KV cache; `generate_with_latents()` additionally extends that cache by the TRAJ tokens, which replaces the reference's
 second full prefill in `generate_latents(output_ids, ...)` (policy L187-190).
 
-`forward()` is the training forward of the navdp_async branch on a collated batch, forward only (no backward kernels yet).
+`forward()` is the training forward of the navdp_async branch on a collated batch (the backward lives in train_step.py).
 
-Not built yet: the NextDiT System-1 branch and the backward pass -- there is no fallback for either.
+`system1 = "nextdit_async"` (the released DualVLN head: trajectory DiT + flow matching, nextdit.py) is served through the
+same `generate_traj`; its training branch is not built (the training step is the navdp_async one, train_step.py).
 """
 from types import SimpleNamespace
 
@@ -30,8 +31,9 @@ IMAGE_TOKEN_INDEX = 151655
 class _Model:
     """Stands in for `InternVLAN1Model` (= `.model` / `.get_model()` of the reference class)."""
 
-    def __init__(self, navdp, s2, config):
-        self.navdp = navdp
+    def __init__(self, navdp, s2, config, nextdit=None):
+        self.navdp = navdp          # system1 = "navdp_async"
+        self.nextdit = nextdit      # system1 = "nextdit_async": traj_dit, cond_projector, rgb_model, memory_encoder, ... in one object
         self._s2 = s2
         self.config = config
         self.device = s2.device
@@ -43,18 +45,23 @@ class _Model:
 
 class InternVLAN1ForCausalLM:
     def __init__(self, cfg=None, device="cuda:0", system1="navdp_async", predict_size=32, memory_size=2):
-        if "navdp" not in system1:
-            raise NotImplementedError("n1b200 implements the NavDP System-1 head (system1='navdp_async'); "
-                                      "NextDiT is listed under SURVEY.md §8f")
+        if system1 not in ("navdp_async", "nextdit_async"):
+            raise NotImplementedError("n1b200 implements system1 = 'navdp_async' and 'nextdit_async' (the reference's two "
+                                      "asynchronous System-1 heads); got %r" % (system1,))
         self.cfg = dict(QWEN25VL_7B if cfg is None else cfg)
         self.device = torch.device(device)
         self.config = SimpleNamespace(system1=system1, n_query=self.cfg["n_query"], use_cache=True,
                                       hidden_size=self.cfg["hidden"], image_token_id=IMAGE_TOKEN_INDEX)
         self._s2 = System2(self.cfg, device=device)
-        navdp = NavDP_Policy_DPT_CriticSum_DAT(memory_size=memory_size, predict_size=predict_size,
-                                               vlm_token_dim=self.cfg["hidden"], navdp_version=0.1, device=device,
-                                               n_query=self.cfg["n_query"])
-        self.model = _Model(navdp, self._s2, self.config)
+        navdp = nextdit = None
+        if "navdp" in system1:
+            navdp = NavDP_Policy_DPT_CriticSum_DAT(memory_size=memory_size, predict_size=predict_size,
+                                                   vlm_token_dim=self.cfg["hidden"], navdp_version=0.1, device=device,
+                                                   n_query=self.cfg["n_query"])
+        else:
+            from .nextdit import NextDiTSystem1
+            nextdit = NextDiTSystem1(device=device)
+        self.model = _Model(navdp, self._s2, self.config, nextdit)
 
     @classmethod
     def from_pretrained(cls, model_path, torch_dtype=None, attn_implementation=None, device_map=None, device=None, **kw):
@@ -94,13 +101,20 @@ class InternVLAN1ForCausalLM:
         and `model.navdp.*`).  `lm_head.*` is ignored (generate_latents never uses it)."""
         navdp_sd = {k[len("model.navdp."):]: v for k, v in state_dict.items() if k.startswith("model.navdp.")}
         rest = {k: v for k, v in state_dict.items() if not k.startswith("model.navdp.")}
+        if self.model.nextdit is not None:
+            # the NextDiT modules hang directly off `.model` in the reference (internvla_n1_arch.py L131-145)
+            heads = ("cond_projector.", "rgb_model.", "memory_encoder.", "rgb_resampler.", "action_encoder.", "action_decoder.",
+                     "traj_dit.")
+            dit_sd = {k[len("model."):]: v for k, v in rest.items() if k.startswith("model.") and k[len("model."):].startswith(heads)}
+            rest = {k: v for k, v in rest.items() if not (k.startswith("model.") and k[len("model."):].startswith(heads))}
+            self.model.nextdit.load_state_dict(dit_sd)
         self._s2.load_state_dict(rest)
         if navdp_sd:
             self.model.navdp.load_state_dict(navdp_sd)
 
-    def load_parts(self, s2_state_dict, navdp_state_dict):
+    def load_parts(self, s2_state_dict, system1_state_dict):
         self._s2.load_state_dict(s2_state_dict)
-        self.model.navdp.load_state_dict(navdp_state_dict)
+        (self.model.navdp if self.model.nextdit is None else self.model.nextdit).load_state_dict(system1_state_dict)
 
     # ------------------------------------------------------------------ hot path
     @staticmethod
@@ -118,7 +132,13 @@ class InternVLAN1ForCausalLM:
 
     def generate_traj(self, traj_latents, images_dp, depths_dp=None, predict_step_nums=32, guidance_scale=1.0,
                       num_inference_steps=10, num_sample_trajs=32, x_init=None, step_noise=None):
-        """internvla_n1.py L349-441, navdp branch (L434-441): -> [num_sample_trajs * B, predict_size, 3]."""
+        """internvla_n1.py L349-441: the nextdit branch (L359-432, flow-matching Euler over the trajectory DiT with
+        classifier-free guidance) or the navdp branch (L434-441) -> [num_sample_trajs * B, predict_size, 3]."""
+        if self.model.nextdit is not None:
+            return self.model.nextdit.generate_traj(traj_latents.to(self.device), images_dp, depths_dp,
+                                                    predict_step_nums=predict_step_nums, guidance_scale=guidance_scale,
+                                                    num_inference_steps=num_inference_steps,
+                                                    num_sample_trajs=num_sample_trajs, x_init=x_init)
         return self.model.navdp.predict_pointgoal_action_async(
             traj_latents.to(self.device), images_dp, depths_dp, sample_num=num_sample_trajs, x_init=x_init,
             step_noise=step_noise)

@@ -89,8 +89,8 @@ def condition_tokens(sd, traj_latents, images_dp):
     lat = _lin(sd, "cond_projector.2", F.gelu(_lin(sd, "cond_projector.0", traj_latents), approximate="tanh"))
     B = images_dp.shape[0]
     img = images_dp.permute(0, 1, 4, 2, 3)
-    mean = torch.tensor(RESNET_MEAN, dtype=torch.float32).view(1, 1, 3, 1, 1)
-    std = torch.tensor(RESNET_STD, dtype=torch.float32).view(1, 1, 3, 1, 1)
+    mean = torch.tensor(RESNET_MEAN, dtype=torch.float32, device=img.device).view(1, 1, 3, 1, 1)
+    std = torch.tensor(RESNET_STD, dtype=torch.float32, device=img.device).view(1, 1, 3, 1, 1)
     img = ((img - mean) / std).flatten(0, 1).to(dtype)
     feat = N.dinov2_vits(sd, "rgb_model.", img).unflatten(0, (B, -1)).flatten(1, 2)      # [B, 512, 384]
     mem = memory_encoder(sd, feat)
@@ -103,7 +103,7 @@ def condition_tokens(sd, traj_latents, images_dp):
 def timestep_sinusoid(t, dim=256, max_period=10000):
     """get_timestep_embedding(t, 256, flip_sin_to_cos=True, downscale_freq_shift=0.0, scale=1)."""
     half = dim // 2
-    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat((torch.cos(emb), torch.sin(emb)), dim=-1)
 
@@ -157,7 +157,7 @@ def traj_dit(sd, x, timestep, z_latents, p="traj_dit.model."):
     L296-368): x [n, 32, 384], timestep [n], z_latents [n, 36, 768] -> [n, 32, 384]."""
     enc = _lin(sd, p + "caption_projection.linear_2",
                F.gelu(_lin(sd, p + "caption_projection.linear_1", z_latents), approximate="tanh"))
-    mask = torch.ones(z_latents.shape[0], z_latents.shape[1])
+    mask = torch.ones(z_latents.shape[0], z_latents.shape[1], device=z_latents.device)
     temb = time_caption_embed(sd, p + "time_caption_embed.", timestep, enc, mask)
     for i in range(LAYERS):
         x = dit_block(sd, "%slayers.%d." % (p, i), x, enc, temb)
@@ -184,7 +184,7 @@ def action_features(sd, latents):
     half = DIM // 2
     freqs = torch.arange(T, dtype=torch.float32)[:, None] * torch.exp(
         -torch.arange(half, dtype=torch.float) * (torch.log(torch.tensor(10000.0)) / half))[None, :]
-    pos = torch.cat((torch.sin(freqs), torch.cos(freqs)), dim=-1)
+    pos = torch.cat((torch.sin(freqs), torch.cos(freqs)), dim=-1).to(latents.device)
     f = _lin(sd, "action_encoder", latents)
     return f + pos.to(f.dtype)[None]
 
@@ -199,10 +199,10 @@ def generate_traj(sd, traj_latents, images_dp, x_init, guidance_scale=1.0, num_i
     for i, t in enumerate(timesteps):
         feats = action_features(sd, latents)
         inp = feats.repeat(2, 1, 1)
-        tt = t.unsqueeze(0).expand(inp.shape[0]).to(torch.long)
+        tt = t.unsqueeze(0).expand(inp.shape[0]).to(inp.device, torch.long)
         pred = _lin(sd, "action_decoder", traj_dit(sd, inp, tt, hidden_in))
         uncond, cond = pred.chunk(2)
         pred = uncond + guidance_scale * (cond - uncond)
         # FlowMatchEulerDiscreteScheduler.step: fp32 Euler update, cast back to the model dtype
-        latents = (latents.to(torch.float32) + (sigmas[i + 1] - sigmas[i]) * pred).to(pred.dtype)
+        latents = (latents.to(torch.float32) + (sigmas[i + 1] - sigmas[i]).to(pred.device) * pred).to(pred.dtype)
     return latents
