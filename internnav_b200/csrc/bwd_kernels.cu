@@ -223,7 +223,11 @@ constexpr int AQ = 8;  // query rows per tile
 
 // One CTA per (kv sequence, kv head): it alone updates that head's dK / dV rows, looping over the query sequences that
 // share the K/V sequence (kv_div), the query heads of the GQA group and the query tiles.  128 threads.
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
+// `stage`: K and V of the head are first copied into shared memory (bf16, rows padded by one word): every pass below reads
+// them ~(query heads of the group) x (query tiles) times, and the score / dP passes walk them one key per thread -- from
+// global memory those are 2-byte loads 32 rows apart (profiles/r2_launches_ddp_train_v1_summary.txt: 2.5 ms per launch in the
+// System-2 backward, 7 query heads x 304 keys x 128).
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p, const int stage) {
   extern __shared__ float sm[];
   const AttnParams& f = p.f;
   const int hd = f.hd;
@@ -242,6 +246,18 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bf16* gk = f.k + (long)k_start * f.ldk + hk * hd;
   const bf16* gv = f.v + (long)k_start * f.ldv + hk * hd;
+  const int hdp = hd + 2;            // padded row (bf16 elements): consecutive keys fall into consecutive banks
+  bf16* sK16 = reinterpret_cast<bf16*>(sS + AQ * skp);
+  bf16* sV16 = sK16 + (size_t)(stage ? sk : 0) * hdp;
+  if (stage) {
+    for (int i = tid; i < sk * (hd / 2); i += 128) {
+      const int j = i / (hd / 2), c = i % (hd / 2);
+      *reinterpret_cast<uint32_t*>(sK16 + j * hdp + 2 * c) = *reinterpret_cast<const uint32_t*>(gk + (long)j * f.ldk + 2 * c);
+      *reinterpret_cast<uint32_t*>(sV16 + j * hdp + 2 * c) = *reinterpret_cast<const uint32_t*>(gv + (long)j * f.ldv + 2 * c);
+    }
+  }
+  auto Kat = [&](int j, int d) { return stage ? __bfloat162float(sK16[j * hdp + d]) : ldf(gk + (long)j * f.ldk + d); };
+  auto Vat = [&](int j, int d) { return stage ? __bfloat162float(sV16[j * hdp + d]) : ldf(gv + (long)j * f.ldv + d); };
   const int kvd = f.heads_kv * hd;
   float* gdk = p.dk + (long)k_start * kvd + hk * hd;
   float* gdv = p.dv + (long)k_start * kvd + hk * hd;
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
 #pragma unroll
           for (int r = 0; r < AQ; ++r) acc[r] = 0.f;
           for (int d = 0; d < hd; ++d) {
-            const float kv = ldf(gk + (long)j * f.ldk + d);
+            const float kv = Kat(j, d);
 #pragma unroll
             for (int r = 0; r < AQ; ++r) acc[r] += sQ[r * hd + d] * kv;
           }
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
 #pragma unroll
           for (int r = 0; r < AQ; ++r) dp[r] = 0.f;
           for (int d = 0; d < hd; ++d) {
-            const float vv = ldf(gv + (long)j * f.ldv + d);
+            const float vv = Vat(j, d);
 #pragma unroll
             for (int r = 0; r < AQ; ++r) dp[r] += sDO[r * hd + d] * vv;
           }
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
         for (int i = tid; i < nq * hd; i += 128) {
           const int r = i / hd, d = i % hd;
           float acc = 0.f;
-          for (int j = 0; j < sk; ++j) acc += sS[r * skp + j] * ldf(gk + (long)j * f.ldk + d);
+          for (int j = 0; j < sk; ++j) acc += sS[r * skp + j] * Kat(j, d);
           p.dq[(long)(q_start + q0 + r) * p.lddq + h * hd + d] = __float2bfloat16(acc);
         }
         // dK[j, d] += sum_r dS[r, j] Q[r, d] ;  dV[j, d] += sum_r P[r, j] dO[r, d]
@@ -441,14 +457,20 @@ void attention_bwd(const AttnBwdParams& p, cudaStream_t s) {
   const int max_sk = f.k_len ? f.k_slot : (f.cu_k ? f.seq_k /* caller passes the maximum here */ : f.seq_k);
   N1_CHECK(max_sk > 0 && max_sk <= 2048, "attention_bwd: key length must be in (0, 2048] (pass the maximum in seq_k)");
   const int skp = (max_sk + 3) & ~3;
-  const size_t smem = (size_t)(2 * AQ * f.hd + 3 * AQ + 2 * AQ * skp) * sizeof(float);
+  size_t smem = (size_t)(2 * AQ * f.hd + 3 * AQ + 2 * AQ * skp) * sizeof(float);
+  // K / V of one head staged in shared memory when they fit next to the tiles (even head_dim, 4-byte aligned rows)
+  const size_t kv_bytes = (size_t)2 * max_sk * (f.hd + 2) * sizeof(bf16);
+  const bool aligned = f.hd % 2 == 0 && f.ldk % 2 == 0 && f.ldv % 2 == 0 && (reinterpret_cast<uintptr_t>(f.k) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(f.v) & 3) == 0;
+  const int stage = aligned && smem + kv_bytes <= 200 * 1024 ? 1 : 0;
+  if (stage) smem += kv_bytes;
   static size_t attr = 0;
   if (smem > attr) {
     N1_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   dim3 grid(f.batch / f.kv_div, f.heads_kv);
-  attn_bwd_kernel<<<grid, 128, smem, s>>>(p);
+  attn_bwd_kernel<<<grid, 128, smem, s>>>(p, stage);
   prof_count_launch();
   N1_CUDA(cudaGetLastError());
 }
