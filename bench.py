@@ -39,6 +39,10 @@ WORKLOADS = {
                        desc="configs[2]: System-2 VLM forward only (Qwen2.5-VL-7B ViT + LLM prefill -> 4 latent tokens), "
                             "32 frames (392x392 -> 784 patches -> 196 tokens) x 80-token instruction + 24 template tokens + "
                             "4 latent queries = 304 tokens per env, bf16"),
+    "nextdit_traj": dict(kind="nextdit", B=64, Ns=32, T=32, K=10,
+                         desc="NextDiT System 1 (system1 = nextdit_async, the released DualVLN head): 64 envs x 32 trajectories "
+                              "of horizon 32, condition tokens (DINOv2 ViT-S on 2 frames + MemoryEncoder + QFormer + latent "
+                              "projection) + 10 flow-matching Euler steps of the 12-block trajectory DiT, guidance 1.0, bf16"),
     "ddp_train": dict(kind="train", B=32, f=6, S=304, grid=(1, 28, 28), T=32, K=20, Ns=1,
                       desc="configs[4]: InternVLA-N1 DDP training step (navdp_async branch), 32 episodes per GPU (global "
                            "batch 256 on 8 GPUs), S = 304 tokens (1 frame 392x392 + 104 text + 4 TRAJ), f = 6 selected "
@@ -216,6 +220,8 @@ def run_ours(args, wl):
         return run_ours_s2(args, wl)
     if wl["kind"] == "train":
         return run_ours_train(args, wl)
+    if wl["kind"] == "nextdit":
+        return run_ours_nextdit(args, wl)
     return run_ours_denoise(args, wl)
 
 
@@ -734,6 +740,103 @@ def run_ours_denoise(args, wl):
              "d2h_bytes_per_step": B * 65 * 4,
              "api": "NavDP_Policy_DPT_CriticSum_DAT.sample + batched_traj_to_actions (device action tail), pinned host inputs"},
             denoise_flops_per_sample_step(T) * R * K)
+
+
+def nextdit_flops(B, Ns, T, steps, halves=1):
+    """Matrix-product + attention FLOPs of one NextDiT call: condition tokens per environment + sampler per trajectory row."""
+    D, L, F = 384, 768, 1024
+    vit = 2 * 257 * (12 * (4 * D * D + 8 * D * D) + 588 * D) + 12 * 4 * 257 * 257 * D
+    mem = 3 * (512 * 2 * (4 * D * D + 2 * D * 2048) + 4 * 512 * 512 * D)
+    qf = 3 * (32 * 2 * (4 * L * L + 2 * L * 2048 + 2 * L * L) + 512 * 2 * 2 * L * L + 4 * 32 * 32 * L + 4 * 32 * 512 * L)
+    cond = 2 * vit + mem + qf + 4 * 2 * (3584 * L + L * L)
+    row = 12 * 2 * (5 * D * D + 3 * D * F) + 12 * (4 * T * D + 4 * 36 * D)      # per trajectory token and evaluation
+    return B * cond + halves * B * Ns * T * steps * row
+
+
+def run_ours_nextdit(args, wl):
+    import torch.distributed as dist
+    from internnav_b200 import _lib
+    from internnav_b200.manifest import random_nextdit_state_dict
+    from internnav_b200.nextdit import NextDiTSystem1
+    from internnav_b200.postprocess import batched_traj_to_actions
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Ns, T, K = wl["B"], wl["Ns"], wl["T"], wl["K"]
+    model = NextDiTSystem1(device=str(dev), num_inference_steps=K).load_state_dict(random_nextdit_state_dict(0))
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    h_lat = torch.randn(B, 4, 3584, generator=g).bfloat16().pin_memory()
+    h_img = torch.rand(B, 2, 224, 224, 3, generator=g).pin_memory()
+    h_x0 = torch.randn(B * Ns, T, 3, generator=g).bfloat16().pin_memory()
+    d_lat, d_img, d_x0 = (t.to(dev) for t in (h_lat, h_img, h_x0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        return model.generate_traj(d_lat, d_img, None, T, 1.0, K, Ns, x_init=d_x0)
+
+    def step_e2e():
+        traj = model.generate_traj(h_lat.to(dev, non_blocking=True), h_img.to(dev, non_blocking=True), None, T, 1.0, K, Ns,
+                                   x_init=h_x0.to(dev, non_blocking=True))
+        return batched_traj_to_actions(traj.float(), B, max_actions=4)     # device action tail, D2H = the ids
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, use_events=True):
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            if use_events:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            else:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                tot += (time.perf_counter() - t0) * 1e3
+        return tot
+
+    for _ in range(max(args.warmup, MIN_WARMUP)):     # also captures the sampler's CUDA graph (profiler off)
+        step_resident()
+    _lib.prof_read()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    barrier()
+    launches = _lib.prof_read()
+    clocks = clk.summary()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps, use_events=False)
+    barrier()
+    _lib.prof_read()
+    _lib.prof_enable(True)                             # roofline pass: eager launches with per-GEMM events, untimed
+    model.sample(model.condition_tokens(d_lat, d_img), d_x0, 1.0, K, Ns, graph=False)
+    torch.cuda.synchronize()
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    launches["total_launches"] //= max(args.steps, 1)
+    _finish(args, wl, world, rank, dev, ms, ms_e2e, launches, clocks, prof, B,
+            {"samples_per_env": Ns, "horizon": T, "euler_steps": K, "guidance_scale": 1.0,
+             "launch_mode": "condition tokens eager, sampler = CUDA graph replay (eager for the roofline pass)",
+             "weights": "random-init NextDiT System 1 (91.4M params)", "launches_are": "per step"},
+            {"h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in (h_lat, h_img, h_x0)), "d2h_bytes_per_step": B * 65 * 4,
+             "api": "NextDiTSystem1.generate_traj + batched_traj_to_actions (device action tail), pinned host inputs"},
+            nextdit_flops(B, Ns, T, K))
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs

@@ -295,33 +295,17 @@ int n1_prof_read_shapes(int32_t* mnk, int64_t* count, double* ms, int cap);
 
 /* ------------------------------------------------------------------------------------------------ kernel-level ops
  * (unit-test / profiling entry points; the model calls above are built from these) */
-/* out[M, N'] = epi(A[M,K] @ W[N,K]^T): act 0 none, 1 gelu(erf), 2 relu, 3 swiglu (W rows interleaved, N' = N/2) */
+/* out[M, N'] = epi(A[M,K] @ W[N,K]^T): act 0 none, 1 gelu(erf), 2 relu, 3 swiglu (W rows interleaved, N' = N/2),
+ * 4 gelu(tanh), 5 silu */
 int n1_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, void* out, int ldo, int M, int N, int K,
                const float* bias, const float* gamma, const void* residual_bf16, int ldr, int act, int out_fp32,
                void* stream);
-/* Full-row GEMM, N = 384: out = [gamma *] (A @ W^T + bias) + residual, and (ln_out != NULL) ln_out = LayerNorm(out).
- * Replaces out_proj / linear2 + residual followed by the next LayerNorm of the NavDP decoder layer (navdp.py L57-66).
- * out must not alias residual when ln_out is given. */
-int n1_op_gemm_row384(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int K, const float* bias,
-                      const float* gamma, const void* residual_bf16, int ldr, void* out_bf16, int ldo,
-                      const float* ln_w, const float* ln_b, float ln_eps, void* ln_out_bf16, int ld_ln, void* stream);
-/* NavDP decoder FF block in one kernel: out = residual + W2 GELU(W1 x + b1) + b2; x [M,384], W1 [1536,384], W2 [384,1536]
- * (replaces linear1 / gelu / linear2 / residual of nn.TransformerDecoderLayer, navdp.py L57-66).  cluster: 1 or 2. */
-int n1_op_fused_mlp(const void* x_bf16, int ldx, const void* w1_bf16, const float* b1, const void* w2_bf16,
-                    const float* b2, const void* residual_bf16, int ldr, void* out_bf16, int ldo, int M, int cluster,
-                    void* stream);
 /* NavDP decoder FF block with its LayerNorm, residual stream resident in tensor memory (ff_block.cu):
  * out = x + W2 GELU(W1 LayerNorm(x; ln_w, ln_b, eps) + b1) + b2 -- norm3 / linear1 / GELU / linear2 / residual of
  * nn.TransformerDecoderLayer(norm_first=True), navdp.py L57-66.  x, out bf16 [M, 384] (may alias).  cluster: 1 or 2. */
 int n1_op_ff_block(const void* x_bf16, int ldx, const float* ln_w, const float* ln_b, float eps, const void* w1_bf16,
                    const float* b1, const void* w2_bf16, const float* b2, void* out_bf16, int ldo, int M, int cluster,
                    void* stream);
-/* weight-streaming GEMM for M <= 64 rows (decode passes): out bf16 [M, N or N/2 for SwiGLU]; bias fp32 [N] / residual
- * bf16 [M, ldr] may be NULL; act: 0 none, 1 GELU, 2 ReLU, 3 SwiGLU (tcgen05 GEMM only: 4 tanh-GELU, 5 SiLU); ws: n1_op_gemm_skinny_workspace_bytes() of scratch */
-size_t n1_op_gemm_skinny_workspace_bytes(void);
-int n1_op_gemm_skinny(const void* a_bf16, int lda, const void* w_bf16, int ldw, void* out_bf16, int ldo, int M, int N,
-                      int K, const void* bias_f32, const void* residual_bf16, int ldr, int act, void* ws, size_t ws_bytes,
-                      void* stream);
 int n1_op_layernorm(const void* x_bf16, int ldx, void* y_bf16, int ldy, const float* w, const float* b, int rows, int D,
                     float eps, int rms, void* stream);
 /* Row kernels of the NextDiT System 1 (reference: nextdit_traj.py L125-178 LuminaNextDiTBlock.forward, L352-356;

@@ -64,15 +64,8 @@ SYMBOLS = {
                                     ctypes.POINTER(ctypes.c_double), c_int]),
     "n1_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_int, c_void_p]),
-    "n1_op_gemm_row384": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                                  c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
-    "n1_op_fused_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                c_int, c_int, c_void_p]),
     "n1_op_ff_block": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_void_p]),
-    "n1_op_gemm_skinny_workspace_bytes": (c_size_t, []),
-    "n1_op_gemm_skinny": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                  c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "n1_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int,
                                 c_void_p]),
     "n1_op_mod_norm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
@@ -172,23 +165,6 @@ def gemm(a, w, bias=None, gamma=None, residual=None, act=ACT_NONE, out_fp32=Fals
     return out
 
 
-def gemm_skinny(a, w, bias=None, residual=None, act=ACT_NONE, ws=None):
-    """Weight-streaming product for M <= 64 rows (decode passes): same result contract as gemm()."""
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
-    M, K = a.shape
-    N = w.shape[0]
-    out = torch.empty(M, N // 2 if act == ACT_SWIGLU else N, device=a.device, dtype=torch.bfloat16)
-    nb = lib().n1_op_gemm_skinny_workspace_bytes()
-    if ws is None:
-        ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
-    assert a.stride(1) == 1 and w.stride(1) == 1
-    check(lib().n1_op_gemm_skinny(c_void_p(a.data_ptr()), a.stride(0), c_void_p(w.data_ptr()), w.stride(0), ptr(out),
-                                  out.stride(0), M, N, K, ptr(bias),
-                                  c_void_p(residual.data_ptr()) if residual is not None else None,
-                                  residual.stride(0) if residual is not None else 0, act, ptr(ws), nb, stream_ptr()))
-    return out
-
-
 def layernorm(x, w, b=None, eps=1e-5, rms=False, out=None):
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else out
@@ -274,19 +250,6 @@ def attention_varlen(q, k, v, heads_q, heads_kv, head_dim, cu_seqlens, max_seq, 
     return o, bool(used.value)
 
 
-def fused_mlp(x, w1, b1, w2, b2, residual=None, out=None, cluster=2):
-    """out = residual + gelu(x @ w1.T + b1) @ w2.T + b2 for the NavDP decoder widths (384 -> 1536 -> 384)."""
-    assert x.dtype == torch.bfloat16 and x.shape[1] == 384 and w1.shape == (1536, 384) and w2.shape == (384, 1536)
-    assert w1.is_contiguous() and w2.is_contiguous() and x.stride(1) == 1
-    if out is None:
-        out = torch.empty(x.shape[0], 384, device=x.device, dtype=torch.bfloat16)
-    check(lib().n1_op_fused_mlp(c_void_p(x.data_ptr()), x.stride(0), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
-                                c_void_p(residual.data_ptr()) if residual is not None else None,
-                                residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
-                                out.stride(0), x.shape[0], cluster, stream_ptr()))
-    return out
-
-
 def ff_block(x, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, out=None, cluster=2):
     """out = x + gelu(LayerNorm(x) @ w1.T + b1) @ w2.T + b2 (NavDP decoder FF block, residual stream in tensor memory)."""
     assert x.dtype == torch.bfloat16 and x.shape[1] == 384 and w1.shape == (1536, 384) and w2.shape == (384, 1536)
@@ -296,18 +259,3 @@ def ff_block(x, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, out=None, cluster=2):
     check(lib().n1_op_ff_block(c_void_p(x.data_ptr()), x.stride(0), ptr(ln_w), ptr(ln_b), eps, ptr(w1), ptr(b1), ptr(w2),
                                ptr(b2), c_void_p(out.data_ptr()), out.stride(0), x.shape[0], cluster, stream_ptr()))
     return out
-
-
-def gemm_row384(a, w, bias, gamma=None, residual=None, ln_w=None, ln_b=None, eps=1e-5, out=None):
-    """out = [gamma *] (a @ w.T + bias) + residual (N = 384); with ln_w also returns LayerNorm(out) * ln_w + ln_b."""
-    assert a.dtype == torch.bfloat16 and w.shape[0] == 384 and a.stride(1) == 1 and w.stride(1) == 1
-    M, K = a.shape
-    if out is None:
-        out = torch.empty(M, 384, device=a.device, dtype=torch.bfloat16)
-    ln_out = torch.empty(M, 384, device=a.device, dtype=torch.bfloat16) if ln_w is not None else None
-    check(lib().n1_op_gemm_row384(c_void_p(a.data_ptr()), a.stride(0), c_void_p(w.data_ptr()), w.stride(0), M, K,
-                                  ptr(bias), ptr(gamma), c_void_p(residual.data_ptr()) if residual is not None else None,
-                                  residual.stride(0) if residual is not None else 0, c_void_p(out.data_ptr()),
-                                  out.stride(0), ptr(ln_w), ptr(ln_b), eps, ptr(ln_out),
-                                  ln_out.stride(0) if ln_out is not None else 0, stream_ptr()))
-    return (out, ln_out) if ln_out is not None else out

@@ -580,22 +580,6 @@ int n1_op_gemm(const void* A, int lda, const void* W, int ldw, void* out, int ld
   });
 }
 
-int n1_op_gemm_row384(const void* A, int lda, const void* W, int ldw, int M, int K, const float* bias, const float* gamma,
-                      const void* residual, int ldr, void* out, int ldo, const float* ln_w, const float* ln_b,
-                      float ln_eps, void* ln_out, int ld_ln, void* stream) {
-  return guard([&] {
-    gemm_row384(B16(A), lda, B16(W), ldw, M, K, bias, gamma, B16(residual), ldr, B16(out), ldo, ln_w, ln_b, ln_eps,
-                B16(ln_out), ld_ln, S(stream));
-  });
-}
-
-int n1_op_fused_mlp(const void* x, int ldx, const void* w1, const float* b1, const void* w2, const float* b2,
-                    const void* residual, int ldr, void* out, int ldo, int M, int cluster, void* stream) {
-  return guard([&] {
-    fused_mlp_384(B16(x), ldx, B16(w1), b1, B16(w2), b2, B16(residual), ldr, B16(out), ldo, M, cluster, S(stream));
-  });
-}
-
 int n1_op_ff_block(const void* x, int ldx, const float* ln_w, const float* ln_b, float eps, const void* w1, const float* b1,
                    const void* w2, const float* b2, void* out, int ldo, int M, int cluster, void* stream) {
   return guard([&] {
@@ -603,18 +587,6 @@ int n1_op_ff_block(const void* x, int ldx, const float* ln_w, const float* ln_b,
   });
 }
 
-size_t n1_op_gemm_skinny_workspace_bytes(void) { return gemm_skinny_workspace_bytes(); }
-int n1_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
-                      const void* bias, const void* residual, int ldr, int act, void* ws, size_t ws_bytes, void* stream) {
-  return guard([&] {
-    if (!a || !w || !out || !ws) throw Error(N1_ERR_ARG, "n1_op_gemm_skinny: null pointer");
-    if (ws_bytes < gemm_skinny_workspace_bytes()) throw Error(N1_ERR_WORKSPACE, "n1_op_gemm_skinny: workspace too small");
-    GemmEpilogue e;
-    e.bias = static_cast<const float*>(bias), e.residual = B16(residual), e.ldr = ldr, e.act = act;
-    if (!gemm_skinny_supported(M, N, K, e)) throw Error(N1_ERR_ARG, "n1_op_gemm_skinny: unsupported shape (M <= 64, N % 8, K % 8)");
-    gemm_skinny(B16(a), lda, B16(w), ldw, B16(out), ldo, M, N, K, e, static_cast<float*>(ws), S(stream));
-  });
-}
 int n1_op_mod_norm(const void* x, int ldx, const float* w, const void* mod, int ld_mod, int rows_per_group, const void* res,
                    int ldr, void* out, int ldo, int64_t rows, int D, float eps, int mode, void* stream) {
   return guard([&] {

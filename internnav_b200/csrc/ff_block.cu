@@ -22,7 +22,7 @@
 //       each and multicast it;
 //   final epilogue: TMEM 0..383 -> bf16 -> SMEM staging -> TMA store to x (in place).
 //
-// Differences from the first fused MLP (fused_mlp.cu, kept for reference): LayerNorm inside, residual in TMEM, 16
+// Differences from the first fused MLP of round 1 (removed): LayerNorm inside, residual in TMEM, 16
 // epilogue warps instead of 8 (the GELU epilogue was the limiter: 2 warps per scheduler could not hide FMA latency), and
 // a MUFU-free GELU in packed fp32.
 #include <stdlib.h>

@@ -59,23 +59,6 @@ int device_sm_count();
 CUtensorMap tma_map_2d(const bf16* ptr, long rows, long cols, long ld, int box_rows, int box_cols, bool swizzle);
 void prof_count_gemm(double flops);  // launch + FLOP accounting for GEMM-class kernels outside gemm_tcgen05.cu
 
-// Full-row GEMM for N = 384 with optional fused LayerNorm (gemm_row384.cu):
-//   out = [gamma *] (A @ W^T + bias) + residual ;  ln_out = LayerNorm(out) * ln_w + ln_b  (when ln_out != null)
-void gemm_row384(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const float* bias, const float* gamma,
-                 const bf16* residual, int ldr, bf16* out, int ldo, const float* ln_w, const float* ln_b, float ln_eps,
-                 bf16* ln_out, int ld_ln, cudaStream_t stream);
-
-// Fused MLP of the NavDP decoder (fused_mlp.cu): out = residual + W2 GELU(W1 x + b1) + b2, D = 384, F = 1536.
-void fused_mlp_384(const bf16* x, int ldx, const bf16* w1, const float* b1, const bf16* w2, const float* b2,
-                   const bf16* residual, int ldr, bf16* out, int ldo, int M, int cluster, cudaStream_t stream);
-
-// Weight-streaming GEMM for M <= 64 rows (gemm_skinny.cu): same contract as gemm_bf16 for the epilogues the decode
-// passes use (bias, GELU / ReLU / SwiGLU, residual; bf16 out).  `ws`: gemm_skinny_workspace_bytes() of fp32 scratch.
-bool gemm_skinny_supported(int M, int N, int K, const GemmEpilogue& epi);
-size_t gemm_skinny_workspace_bytes();
-void gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, bf16* out, int ldo, int M, int N, int K,
-                 const GemmEpilogue& epi, float* ws, cudaStream_t stream);
-
 // Launch accounting (always on) and optional per-GEMM event timing (bench.py's roofline pass).
 struct ProfStats {
   double gemm_ms = 0, gemm_flops = 0;

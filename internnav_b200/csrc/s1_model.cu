@@ -32,22 +32,6 @@ void linear(const Lin& L, const bf16* A, int lda, void* out, int ldo, int M, Gem
   gemm_bf16(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, s);
 }
 
-// N1_ROW384: 1 = residual GEMMs of the decoder use the full-row kernel with fused LayerNorm (gemm_row384.cu),
-// 0 (default) = generic GEMM + LayerNorm kernels.  The fused kernel is correct (tests/test_ops_gpu.py) but measured
-// slower on B200 (182 vs 152 us at 65536 x 1536, 67 vs 43 us at 65536 x 384): its single accumulator stage exposes the
-// epilogue, whose per-row residual loads are latency-bound.  Kept for the next round.
-int row384_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("N1_ROW384");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode;
-}
-
-// N1_FUSED_MLP: 0 (default) = two GEMMs, 1 = fused kernel, 2 = fused kernel with 2-CTA weight multicast.
-// The fused kernel (fused_mlp.cu) is EXPERIMENTAL and off: it is correct when it completes, but it is slower than the
-// two-GEMM path (GELU issue-bound, ~400 vs ~320 us at 65536 rows) and a rare hang was seen under pytest on B200.
 // N1_FF_BLOCK: 0 = LayerNorm + FF1 + FF2 as three kernels, 1 / 2 = the FF-block kernel (cluster size).  Default 1:
 // validated on B200 (tests/test_ops_gpu.py::test_ff_block, profiles/r2_ff_block_tests_v0.log) and 6 % faster per
 // dual-system step than the three-kernel form (profiles/r2_bench_dual_system_ffblock_v0.json).
@@ -56,15 +40,6 @@ int ff_block_mode() {
   if (mode < 0) {
     const char* e = getenv("N1_FF_BLOCK");
     mode = e ? atoi(e) : 1;
-  }
-  return mode;
-}
-
-int fused_mlp_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("N1_FUSED_MLP");
-    mode = e ? atoi(e) : 0;
   }
   return mode;
 }
@@ -457,24 +432,12 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
   }
   const float scale48 = 1.0f / sqrtf(48.f);
   bf16* xc = d.x;   // current residual stream
-  bf16* xo = d.x2;  // the other buffer
-  const bool fuse_ln = row384_mode() > 0;
-  // residual GEMM (N = 384) + the LayerNorm that follows it, in one kernel when enabled (gemm_row384.cu)
+  // residual GEMM (N = 384) and the LayerNorm that follows it
   auto res_gemm_ln = [&](const Lin& W, const bf16* A, int lda, const LNp* ln) {
-    if (fuse_ln) {
-      if (ln) {
-        gemm_row384(A, lda, W.w, W.ldw, (int)R, W.K, W.b, nullptr, xc, D, xo, D, ln->w, ln->b, 1e-5f, d.ln, D, s);
-        bf16* t = xc;
-        xc = xo, xo = t;
-      } else {
-        gemm_row384(A, lda, W.w, W.ldw, (int)R, W.K, W.b, nullptr, xc, D, xc, D, nullptr, nullptr, 0.f, nullptr, 0, s);
-      }
-    } else {
-      GemmEpilogue res;
-      res.residual = xc, res.ldr = D;
-      linear(W, A, lda, xc, D, (int)R, res, s);
-      if (ln) layernorm(xc, D, d.ln, D, ln->w, ln->b, (int)R, D, 1e-5f, 0, s);
-    }
+    GemmEpilogue res;
+    res.residual = xc, res.ldr = D;
+    linear(W, A, lda, xc, D, (int)R, res, s);
+    if (ln) layernorm(xc, D, d.ln, D, ln->w, ln->b, (int)R, D, 1e-5f, 0, s);
   };
   layernorm(xc, D, d.ln, D, dec_[0].n1.w, dec_[0].n1.b, (int)R, D, 1e-5f, 0, s);
   for (int l = 0; l < dims.layers; ++l) {
@@ -507,9 +470,6 @@ void S1Model::decoder_pass(const DenoiseBufs& d, const float* x_t, const int* ts
     const LNp* next_ln = l + 1 < dims.layers ? &dec_[l + 1].n1 : nullptr;  // the head applies the final LayerNorm itself
     if (ffb) {
       ff_block_384(xc, D, L.n3.w, L.n3.b, 1e-5f, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, xc, D, (int)R, ff_block_mode(), s);
-      if (next_ln) layernorm(xc, D, d.ln, D, next_ln->w, next_ln->b, (int)R, D, 1e-5f, 0, s);
-    } else if (fused_mlp_mode() > 0 && L.ff1.N == 1536 && L.ff1.ldw == D && L.ff2.ldw == 1536) {
-      fused_mlp_384(d.ln, D, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, xc, D, xc, D, (int)R, fused_mlp_mode(), s);
       if (next_ln) layernorm(xc, D, d.ln, D, next_ln->w, next_ln->b, (int)R, D, 1e-5f, 0, s);
     } else {
       GemmEpilogue gelu;

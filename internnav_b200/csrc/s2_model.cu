@@ -466,25 +466,12 @@ struct S2Model::GenBufs {
   int *cur_tok, *gen, *finished, *next, *k_len, *n_active, *out_tokens, *dest, *pos3, *kind, *src;
   float2* rope;
   bf16 *x, *ln, *qkv, *att, *hid, *normed, *logits;
-  float* skinny = nullptr;  // fp32 scratch of the weight-streaming GEMM (null: every product goes through gemm_bf16)
 };
 
 namespace {
-// N1_SKINNY_GEMM=1 routes the M <= 64 products of the decode passes through gemm_skinny.cu.  Default 0 until the kernel
-// has a GPU parity run on record (profiles/).
-int skinny_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("N1_SKINNY_GEMM");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode;
-}
-void linear_rows(const Lin& L, const bf16* A, int lda, bf16* out, int ldo, int M, GemmEpilogue e, float* skinny_ws,
-                 cudaStream_t s) {
+void linear_rows(const Lin& L, const bf16* A, int lda, bf16* out, int ldo, int M, GemmEpilogue e, cudaStream_t s) {
   e.bias = L.b;
-  if (skinny_ws && gemm_skinny_supported(M, L.N, L.K, e)) gemm_skinny(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, skinny_ws, s);
-  else gemm_bf16(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, s);
+  gemm_bf16(A, lda, L.w, L.ldw, out, ldo, M, L.N, L.K, e, s);
 }
 }  // namespace
 
@@ -497,7 +484,7 @@ void S2Model::chunk_pass(const GenBufs& g, const LlmPlan& p, const KvCache& kv, 
   for (int l = 0; l < dims.layers; ++l) {
     const LBlock& b = lblk_[l];
     layernorm(g.x, H, g.ln, H, b.n1, nullptr, R, H, dims.rms_eps, 1, s);
-    linear_rows(b.qkv, g.ln, H, g.qkv, qkv_n, R, GemmEpilogue(), g.skinny, s);
+    linear_rows(b.qkv, g.ln, H, g.qkv, qkv_n, R, GemmEpilogue(), s);
     apply_rope(g.qkv, qkv_n, g.rope, R, dims.heads + dims.kv_heads, hd, s);
     bf16* ck = kv.k + l * kv.layer_stride;
     bf16* cv = kv.v + l * kv.layer_stride;
@@ -511,12 +498,12 @@ void S2Model::chunk_pass(const GenBufs& g, const LlmPlan& p, const KvCache& kv, 
     attention(a, s);
     GemmEpilogue res;
     res.residual = g.x, res.ldr = H;
-    linear_rows(b.o, g.att, H, g.x, H, R, res, g.skinny, s);
+    linear_rows(b.o, g.att, H, g.x, H, R, res, s);
     layernorm(g.x, H, g.ln, H, b.n2, nullptr, R, H, dims.rms_eps, 1, s);
     GemmEpilogue sw;
     sw.act = ACT_SWIGLU;
-    linear_rows(b.gateup, g.ln, H, g.hid, inter_pad_, R, sw, g.skinny, s);
-    linear_rows(b.down, g.hid, inter_pad_, g.x, H, R, res, g.skinny, s);
+    linear_rows(b.gateup, g.ln, H, g.hid, inter_pad_, R, sw, s);
+    linear_rows(b.down, g.hid, inter_pad_, g.x, H, R, res, s);
   }
   layernorm(g.x, H, g.normed, H, final_norm_, nullptr, R, H, dims.rms_eps, 1, s);
 }
@@ -538,7 +525,6 @@ size_t S2Model::gen_impl(Carver c, const LlmPlan& p, const bf16* image_feats, co
   g.x = c.take<bf16>((size_t)R5 * H), g.ln = c.take<bf16>((size_t)R5 * H), g.qkv = c.take<bf16>((size_t)R5 * qkv_n);
   g.att = c.take<bf16>((size_t)R5 * H), g.hid = c.take<bf16>((size_t)R5 * inter_pad_);
   g.normed = c.take<bf16>((size_t)R5 * H), g.logits = c.take<bf16>((size_t)B * dims.vocab);
-  if (skinny_mode() && B <= 64) g.skinny = c.take<float>(gemm_skinny_workspace_bytes() / sizeof(float));
   if (c.dry()) return llm_impl(c, p, nullptr, nullptr, nullptr, &kv);  // prefill scratch follows the decode state
 
   // 1. prompt prefill, K/V kept; final-norm state of the last prompt token of each sequence -> g.normed [B, H]
@@ -550,7 +536,7 @@ size_t S2Model::gen_impl(Carver c, const LlmPlan& p, const bf16* image_feats, co
   int steps = 0;
   for (int it = 0; it < p.max_new; ++it) {
     // logits = lm_head(hidden[:, -1]) in bf16, next = argmax (GenerationMixin greedy search)
-    linear_rows(lm_head_, g.normed, H, g.logits, dims.vocab, B, GemmEpilogue(), g.skinny, s);
+    linear_rows(lm_head_, g.normed, H, g.logits, dims.vocab, B, GemmEpilogue(), s);
     argmax_rows(g.logits, dims.vocab, dims.vocab, B, g.next, s);
     gen_update(g.next, g.cur_tok, g.gen, g.finished, g.out_tokens, p.max_new, eos, n_eos, B, g.n_active, s);
     int active = 0;
