@@ -272,6 +272,12 @@ int n1_traj_to_actions(const void* traj_f32, int B, int Ns, int T, double turn_a
  * products of the training step (action embedding / head, navdp.py L79, L186; position-table resample, dinov2.py L180-211) */
 int n1_op_sgemm(const void* A_f32, int lda, int trans_a, const void* B_f32, int ldb, int trans_b, void* C_f32, int ldc, int M,
                 int N, int K, int accumulate, void* stream);
+/* Weight gradient dW[No, Ko] (+)= dY[M, No]^T X[M, Ko] (bf16 operands read in place, rows 16-byte aligned, Ko % 4 == 0; fp32
+ * out contiguous): what autograd computes for `weight.grad` of every nn.Linear of the trainable System-1 branches.
+ * ws: n1_op_wgrad_workspace_bytes(M, No, Ko) bytes of 16-byte aligned scratch (partial tiles of the row splits). */
+size_t n1_op_wgrad_workspace_bytes(int M, int No, int Ko);
+int n1_op_wgrad(const void* dy_bf16, int ld_dy, const void* x_bf16, int ld_x, int M, int No, int Ko, void* out_f32,
+                int accumulate, void* ws, size_t ws_bytes, void* stream);
 /* out[r, c] = x[r, c] * gamma[c] (+ add[r, c]): LayerScale forward / backward with the residual add (layer_scale.py L27-28) */
 int n1_op_scale_cols(const void* x_bf16, int ld_x, const void* gamma_f32, const void* add_bf16_or_null, int ld_add,
                      void* out_bf16, int ld_out, int64_t rows, int cols, void* stream);

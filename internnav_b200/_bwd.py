@@ -14,7 +14,7 @@ from ._lib import check, ptr, stream_ptr
 _bound = False
 BWD_SYMBOLS = ["n1_op_act_fwd", "n1_op_transpose", "n1_op_colsum", "n1_op_norm_bwd", "n1_op_act_bwd", "n1_op_swiglu_bwd",
                "n1_op_rope_transposed", "n1_op_attention_bwd", "n1_op_adamw", "n1_op_sgemm", "n1_op_scale_cols",
-               "n1_op_patchify_depth"]
+               "n1_op_patchify_depth", "n1_op_wgrad"]
 
 
 def _L():
@@ -35,6 +35,9 @@ def _L():
         L.n1_op_sgemm.argtypes = [vp, c_int, c_int, vp, c_int, c_int, vp, c_int, c_int, c_int, c_int, c_int, vp]
         L.n1_op_scale_cols.argtypes = [vp, c_int, vp, vp, c_int, vp, c_int, c_int64, c_int, vp]
         L.n1_op_patchify_depth.argtypes = [vp, vp, c_int, c_int, vp]
+        L.n1_op_wgrad.argtypes = [vp, c_int, vp, c_int, c_int, c_int, c_int, vp, c_int, vp, ctypes.c_size_t, vp]
+        L.n1_op_wgrad_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        L.n1_op_wgrad_workspace_bytes.restype = ctypes.c_size_t
         for n in BWD_SYMBOLS:
             getattr(L, n).restype = c_int
         _bound = True
@@ -108,6 +111,33 @@ def attention_bwd(q, k, v, o, dout, heads_q, heads_kv, head_dim, batch, seq_q, s
                                    head_dim, batch, seq_q, seq_k, ptr(cu_q), ptr(cu_k), max_seq_q, kv_div,
                                    1 if causal else 0, scale, ptr(k_len), k_slot, stream_ptr()))
     return dq, dk, dv
+
+
+def wgrad_supported(dy, x):
+    """Operands the in-place weight-gradient kernel takes: bf16 rows with 16-byte aligned starts and pitches, Ko % 4 == 0."""
+    import os
+    if os.environ.get("N1_WGRAD_TN", "1") == "0":     # keep the transposing path (A/B comparison)
+        return False
+    return (dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.dim() == 2 and x.dim() == 2
+            and dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1 and dy.stride(0) % 8 == 0
+            and x.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0 and x.shape[1] % 4 == 0
+            and dy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0)
+
+
+def wgrad(dy, x, out=None, accumulate=False):
+    """dW [No, Ko] fp32 (+)= dy[M, No]^T @ x[M, Ko], operands read in place (csrc/wgrad_tn.cu)."""
+    assert wgrad_supported(dy, x), (dy.shape, dy.stride(), x.shape, x.stride())
+    M, No, Ko = dy.shape[0], dy.shape[1], x.shape[1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty(No, Ko, dtype=torch.float32, device=dy.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (No, Ko)
+    L = _L()
+    nb = L.n1_op_wgrad_workspace_bytes(M, No, Ko)
+    ws = torch.empty(nb + 16, dtype=torch.uint8, device=dy.device)
+    check(L.n1_op_wgrad(c_void_p(dy.data_ptr()), dy.stride(0), c_void_p(x.data_ptr()), x.stride(0), M, No, Ko, ptr(out),
+                        1 if accumulate else 0, c_void_p((ws.data_ptr() + 15) // 16 * 16), nb, stream_ptr()))
+    return out
 
 
 def sgemm(a, b, trans_a=False, trans_b=False, out=None, accumulate=False):

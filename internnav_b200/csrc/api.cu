@@ -499,6 +499,13 @@ int n1_op_sgemm(const void* A, int lda, int trans_a, const void* B, int ldb, int
                 ldc, M, N, K, accumulate, S(stream));
   });
 }
+size_t n1_op_wgrad_workspace_bytes(int M, int No, int Ko) { return wgrad_tn_workspace_bytes(M, No, Ko); }
+int n1_op_wgrad(const void* dy, int ld_dy, const void* x, int ld_x, int M, int No, int Ko, void* out, int accumulate, void* ws,
+                size_t ws_bytes, void* stream) {
+  return guard([&] {
+    wgrad_tn(B16(dy), ld_dy, B16(x), ld_x, M, No, Ko, static_cast<float*>(out), accumulate, ws, ws_bytes, S(stream));
+  });
+}
 int n1_op_scale_cols(const void* x, int ld_x, const void* gamma, const void* add, int ld_add, void* out, int ld_out,
                      int64_t rows, int cols, void* stream) {
   return guard([&] {

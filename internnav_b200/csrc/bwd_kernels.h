@@ -57,6 +57,12 @@ struct AttnBwdParams {
   float* dv;             // [rows_k, heads_kv * hd]
 };
 void attention_bwd(const AttnBwdParams& p, cudaStream_t s);
+// Weight gradient dW[No, Ko] (+)= dY[M, No]^T X[M, Ko] without operand transposes (wgrad_tn.cu): both operands read in place
+// as MN-major UMMA tiles, the M range split over CTAs, partial tiles summed in a fixed order.  bf16 in, fp32 out.
+int wgrad_tn_splits(int M, int No, int Ko);
+size_t wgrad_tn_workspace_bytes(int M, int No, int Ko);
+void wgrad_tn(const bf16* dy, int ld_dy, const bf16* x, int ld_x, int M, int No, int Ko, float* out, int accumulate, void* ws,
+              size_t ws_bytes, cudaStream_t stream);
 // tensor-core path (attention_bwd_mma.cu): fixed-length MHA, head_dim 48 / 64, one head's operands within shared memory;
 // attention_bwd() takes it whenever it applies (N1_ATTN_BWD_MMA=0 keeps the scalar kernel)
 bool attention_bwd_mma_supported(const AttnBwdParams& p);

@@ -156,7 +156,7 @@ class InternVLAN1ForCausalLM:
                          timesteps=None):
         """The navdp_async branch of the training forward, from the gathered latent states on (internvla_n1.py
         L231-303): traj_hidden_states [B, n_query, H] (the 4 states at t_s_pos); traj_images [B, f, 224, 224, 3];
-        traj_depths [B, f, 224, 224]; traj_poses [B, f, 32, 3]; video_frame_num [B] -> scalar loss (forward only)."""
+        traj_depths [B, f, 224, 224]; traj_poses [B, f, 32, 3]; video_frame_num [B] -> scalar loss (the forward; the backward lives in train_step.py)."""
         B, f = traj_images.shape[:2]
         hs = traj_hidden_states.unsqueeze(1).repeat(1, f, 1, 1).flatten(0, 1)
         loss_mask = torch.arange(f, device=traj_images.device).expand(B, f) < video_frame_num.to(traj_images.device).unsqueeze(1)
@@ -229,8 +229,8 @@ class InternVLAN1ForCausalLM:
                 image_grid_thw=None, traj_images=None, traj_depths=None, video_frame_num=None, traj_poses=None,
                 noise=None, timesteps=None, **hf_kwargs):
         """Training forward of the navdp_async branch (internvla_n1.py L58-318) on a collated batch -> namespace(loss,
-        logits=None, traj_hidden_states).  FORWARD ONLY: there are no backward kernels yet, so the
-        loss carries no graph; `logits` (computed but unused by this branch in the reference, L229) are not produced.
+        logits=None, traj_hidden_states).  This call is the forward (loss value, no autograd graph); the optimisation step --
+        backward kernels, gradient exchange, AdamW -- is `train_step.DualSystemTrainer.step`; `logits` (computed but unused by this branch in the reference, L229) are not produced.
         `noise` / `timesteps` inject the draws of `sample_noise` (navdp.py L165-175) for parity tests."""
         if labels is None or t_s_pos is None or traj_images is None:
             raise NotImplementedError("forward() implements the training branch (labels + t_s_pos + traj_* given); for "

@@ -280,8 +280,8 @@ class NavDP_Policy_DPT_CriticSum_DAT(torch.nn.Module):
     def forward_vlm_traj(self, vlm_tokens, input_images, input_depths, tensor_label_actions,
                          tensor_augment_actions=None, noise=None, timesteps=None):
         """navdp.py L291-312 (the System-1 half of the training forward): one noise prediction per
-        (episode, frame) sample with its own timestep and its own condition.  FORWARD ONLY -- the returned tensors
-        carry no autograd graph (the backward kernels are not built); `noise` / `timesteps` may be passed in, else
+        (episode, frame) sample with its own timestep and its own condition.  The returned tensors carry no autograd graph
+        (the backward of this branch is scheduled by train_s1.S1TrainStep on the library's backward kernels); `noise` / `timesteps` may be passed in, else
         they are drawn like `sample_noise` (navdp.py L165-175).  Returns (noise_pred, noise)."""
         label = tensor_label_actions.flatten(0, 1).to(self._device)
         n = label.shape[0]

@@ -69,6 +69,13 @@ class GpuOps:
     def act_bwd(self, pre, dy, kind):
         return self._bwd.act_bwd(pre, dy, kind)
 
+    def wgrad(self, dy, x):
+        """dy [M, N]^T @ x [M, K] -> fp32 [N, K]: in place on MN-major operand tiles when the rows are aligned
+        (csrc/wgrad_tn.cu), else through two operand transposes and the K-major GEMM."""
+        if self._bwd.wgrad_supported(dy, x):
+            return self._bwd.wgrad(dy, x)
+        return self.mm_nt(self.transpose(dy), self.transpose(x), out_fp32=True)
+
     def sgemm(self, a, b, trans_a=False, trans_b=False):
         """fp32 op(a) @ op(b) on the CUDA cores (narrow / fp32-only products)."""
         return self._bwd.sgemm(a, b, trans_a, trans_b)
@@ -131,8 +138,7 @@ class S1TrainStep:
         if rows is not None:
             W = W[rows]
         dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
-        dyT, xT = self.ops.transpose(dy2), self.ops.transpose(x2)           # [N, Mp], [K, Mp]
-        dW = self.ops.mm_nt(dyT, xT, out_fp32=True)                        # [N, K]
+        dW = self.ops.wgrad(dy2, x2)                                        # [N, K] fp32
         self._acc(g, name + ".weight", dW, rows)
         if (name + ".bias") in self.p32:
             self._acc(g, name + ".bias", self.ops.colsum(dy2), rows)
@@ -275,7 +281,7 @@ class S1TrainStep:
         self._acc(g, p + "pos_embed", dpe)
         dpatch = dt[:, 1:].reshape(-1, C).contiguous()
         Wp = self.p32[p + "patch_embed.proj.weight"]
-        dWf = ops.mm_nt(ops.transpose(dpatch), ops.transpose(patches), out_fp32=True)[:, :196]   # [D, 196], one channel
+        dWf = ops.wgrad(dpatch, patches)[:, :196]                                                # [D, 196], one channel
         # the three input channels are identical, so each channel of the Conv2d weight receives the same gradient
         self._acc(g, p + "patch_embed.proj.weight", dWf.reshape(Wp.shape[0], 1, 14, 14).expand(Wp.shape))
         self._acc(g, p + "patch_embed.proj.bias", ops.colsum(dpatch))

@@ -33,6 +33,14 @@ class TorchOps:
         y = a @ w.t()
         return y + bias if bias is not None else y
 
+    def wgrad(self, dy, x):
+        """dy^T @ x with the kernel's operand constraints (rows of 8-element multiples) or the transposing fallback."""
+        self._count("wgrad")
+        assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1
+        if dy.stride(0) % 8 == 0 and x.stride(0) % 8 == 0 and dy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0:
+            return dy.t() @ x
+        return self.mm_nt(self.transpose(dy), self.transpose(x), out_fp32=True)
+
     def transpose(self, x):
         self._count("transpose")
         assert x.dim() == 2 and x.stride(1) == 1

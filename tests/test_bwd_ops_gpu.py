@@ -125,6 +125,28 @@ def test_attention_bwd(B, Sq, Sk, Hq, Hkv, hd, causal):
         assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
+@pytest.mark.parametrize("M,No,Ko", [(98304, 1536, 384), (6144, 384, 1152), (1000, 384, 200), (777, 392, 64), (64, 128, 128),
+                                      (130, 8, 2048), (12288, 2048, 384)])
+def test_wgrad_in_place_operands(M, No, Ko):
+    """dW = dY^T X with both operands read in place as MN-major UMMA tiles and the rows split over CTAs (wgrad_tn.cu), vs fp32
+    PyTorch on the same bf16 operands; strided operand views (column slices of a wider buffer) and accumulation."""
+    from internnav_b200 import _bwd as K
+    torch.manual_seed(M + No + Ko)
+    dy = torch.randn(M, No, device="cuda").bfloat16()
+    x = torch.randn(M, Ko, device="cuda").bfloat16()
+    ref = dy.float().t() @ x.float()
+    out = K.wgrad(dy, x)
+    assert out.shape == (No, Ko) and _rel(out, ref) < 1e-3, _rel(out, ref)
+    assert torch.equal(K.wgrad(dy, x), out)                      # fixed summation order: bit-reproducible
+    wide_y = torch.randn(M, No + 16, device="cuda").bfloat16()
+    wide_x = torch.randn(M, 2 * Ko + 8, device="cuda").bfloat16()
+    o2 = K.wgrad(wide_y[:, 8:8 + No], wide_x[:, Ko:2 * Ko])
+    assert _rel(o2, wide_y[:, 8:8 + No].float().t() @ wide_x[:, Ko:2 * Ko].float()) < 1e-3
+    acc = torch.ones(No, Ko, device="cuda")
+    K.wgrad(dy, x, out=acc, accumulate=True)
+    assert _rel(acc, ref + 1.0) < 1e-3
+
+
 def test_adamw_matches_torch():
     from internnav_b200 import _bwd as K
     torch.manual_seed(3)

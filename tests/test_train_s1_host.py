@@ -45,4 +45,4 @@ def test_schedule_reproduces_oracle_gradients():
     print("schedule vs oracle: worst parameter gradient", worst, "latent gradient", rel_h, "kernel calls", ops.calls)
     assert rel_h < 2e-3
     # every heavy operation went through the backend
-    assert ops.calls["mm_nt"] > 500 and ops.calls["attention_bwd"] == 12 + 4 + 32 + 1 and ops.calls["norm_bwd"] > 70
+    assert ops.calls["mm_nt"] > 300 and ops.calls["wgrad"] > 150 and ops.calls["attention_bwd"] == 12 + 4 + 32 + 1 and ops.calls["norm_bwd"] > 70
