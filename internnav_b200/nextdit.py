@@ -53,6 +53,40 @@ def _resample_pos_embed(pos_embed, side=16, offset=0.1):
     return torch.cat((pe[:, :1], patch.permute(0, 2, 3, 1).reshape(1, side * side, -1)), dim=1)
 
 
+def flow_match_schedule(n, num_train_timesteps=1000):
+    """FlowMatchEulerDiscreteScheduler().set_timesteps(n, sigmas=np.linspace(1, 1 / n, n)) (internvla_n1.py L395-396; shift
+    1.0, no dynamic shifting): -> (int64 timesteps [n] as the DiT receives them, float32 sigmas [n + 1] with the trailing 0)."""
+    sig = torch.from_numpy(np.linspace(1.0, 1 / n, n).astype(np.float32)).to(torch.float32)
+    return (sig * num_train_timesteps).to(torch.long), torch.cat((sig, torch.zeros(1)))
+
+
+def fold_patch_embed(Wp, bp):
+    """Conv2d(3, 384, 14, stride 14) on (x - mean) / std  ==  im2col(x) @ W'^T + b' with the ImageNet statistics folded in:
+    W' [384, 3 x 200] (196 taps + 4 zero columns per channel, the layout of n1_op_patchify_depth), b' [384]; fp32."""
+    Wp, bp = Wp.float(), bp.float()
+    cols, bias = [], bp.clone()
+    for c in range(3):
+        wc = Wp[:, c].reshape(Wp.shape[0], 196)
+        cols.append(F.pad(wc / RESNET_STD[c], (0, 4)))
+        bias -= (RESNET_MEAN[c] / RESNET_STD[c]) * wc.sum(1)
+    return torch.cat(cols, dim=1), bias.contiguous()
+
+
+def fold_cross_kv(to_k, to_v, ctx_weight, gate, head_dim=64):
+    """Cross-attention of LuminaNextDiTBlock (nextdit_traj.py L149-160) with the constants folded into the projections:
+    K = to_k(RMSNorm(enc) * ctx) = RMSNorm_noweight(enc) @ (to_k * ctx)^T and, because the gate multiplies the attention
+    OUTPUT per head (softmax(..) V_h * tanh(gate_h)), V' = to_v * ctx with its rows of head h scaled by tanh(gate_h)."""
+    ctx = ctx_weight.float()
+    g = torch.tanh(gate.float()).repeat_interleave(head_dim)
+    return to_k.float() * ctx[None, :], to_v.float() * ctx[None, :] * g[:, None]
+
+
+def fold_head(W2, b2, Wd, bd):
+    """action_decoder(norm_out.linear_2(y)) as one [3 -> 8 rows, 384] product (rows 3..7 zero: GEMM N % 8 == 0)."""
+    W2, b2, Wd, bd = W2.float(), b2.float(), Wd.float(), bd.float()
+    return F.pad(Wd @ W2, (0, 0, 0, 5)), F.pad(Wd @ b2 + bd, (0, 5)).contiguous()
+
+
 class NextDiTSystem1:
     """state_dict keys: internnav_b200.manifest.nextdit_shapes() (the reference's attribute paths below `.model`)."""
 
@@ -78,13 +112,8 @@ class NextDiTSystem1:
         for k in ("cond_projector.0", "cond_projector.2"):
             w[k + ".w"], w[k + ".b"] = b16(sd[k + ".weight"]), f32(k + ".bias")
         # DINOv2 ViT-S/14: im2col weight per channel with the ImageNet normalisation folded in
-        Wp, bp = f32("rgb_model.patch_embed.proj.weight"), f32("rgb_model.patch_embed.proj.bias")
-        cols, bias = [], bp.clone()
-        for c in range(3):
-            wc = Wp[:, c].reshape(DIM, 196)
-            cols.append(F.pad(wc / RESNET_STD[c], (0, 4)))
-            bias -= (RESNET_MEAN[c] / RESNET_STD[c]) * wc.sum(1)
-        w["vit.patch.w"], w["vit.patch.b"] = b16(torch.cat(cols, dim=1)), bias.contiguous()
+        Wpe, bpe = fold_patch_embed(f32("rgb_model.patch_embed.proj.weight"), f32("rgb_model.patch_embed.proj.bias"))
+        w["vit.patch.w"], w["vit.patch.b"] = b16(Wpe), bpe
         pos = _resample_pos_embed(f32("rgb_model.pos_embed"))[0]
         w["vit.pos"] = pos[1:].contiguous()                                             # fp32 [256, 384]
         w["vit.cls"] = (f32("rgb_model.cls_token")[0, 0] + pos[0]).to(torch.bfloat16)    # cls token + its position
@@ -120,10 +149,8 @@ class NextDiTSystem1:
             b, q = "%slayers.%d." % (p, i), "dit.%d." % i
             mod_w.append(sd[b + "norm1.linear.weight"].float())
             mod_b.append(sd[b + "norm1.linear.bias"].float())
-            ctx = f32(b + "norm1_context.weight")                                       # RMSNorm weight of the caption
-            gate = torch.tanh(f32(b + "gate")).repeat_interleave(HD)                    # per output column of to_v
-            kv_w.append(f32(b + "attn2.to_k.weight") * ctx[None, :])
-            kv_w.append(f32(b + "attn2.to_v.weight") * ctx[None, :] * gate[:, None])
+            kv_w += list(fold_cross_kv(f32(b + "attn2.to_k.weight"), f32(b + "attn2.to_v.weight"),
+                                       f32(b + "norm1_context.weight"), f32(b + "gate"), HD))
             w[q + "qkvq.w"] = b16(torch.cat([sd[b + "attn1.to_q.weight"], sd[b + "attn1.to_k.weight"],
                                              sd[b + "attn1.to_v.weight"], sd[b + "attn2.to_q.weight"]], dim=0).float())
             for a, n in (("attn1.norm_q", "nq1"), ("attn1.norm_k", "nk1"), ("attn2.norm_q", "nq2"), ("attn2.norm_k", "nk2")):
@@ -137,10 +164,9 @@ class NextDiTSystem1:
         w["dit.mod.w"], w["dit.mod.b"] = b16(torch.cat(mod_w, dim=0)), torch.cat(mod_b).to(dev).contiguous()
         w["dit.kv.w"] = b16(torch.cat(kv_w, dim=0))                                     # [12 * 768, 384]
         # norm_out.linear_2 followed by action_decoder: one [3 -> 8, 384] product
-        W2, b2 = f32(p + "norm_out.linear_2.weight"), f32(p + "norm_out.linear_2.bias")
-        Wd, bd = f32("action_decoder.weight"), f32("action_decoder.bias")
-        w["head.w"] = b16(F.pad(Wd @ W2, (0, 0, 0, 5)))
-        w["head.b"] = F.pad(Wd @ b2 + bd, (0, 5)).contiguous()
+        Wh, bh = fold_head(f32(p + "norm_out.linear_2.weight"), f32(p + "norm_out.linear_2.bias"), f32("action_decoder.weight"),
+                           f32("action_decoder.bias"))
+        w["head.w"], w["head.b"] = b16(Wh), bh
         w["enc.w"], w["enc.b"] = f32("action_encoder.weight"), f32("action_encoder.bias")
         self.w = w
         self._pos_cache = {}
@@ -218,9 +244,7 @@ class NextDiTSystem1:
     def schedule(self, n=None):
         """FlowMatchEulerDiscreteScheduler().set_timesteps(n, sigmas=np.linspace(1, 1 / n, n)) (internvla_n1.py L395-396):
         -> (int64 timesteps [n], float32 sigmas [n + 1])."""
-        n = n or self.num_inference_steps
-        sig = torch.from_numpy(np.linspace(1.0, 1 / n, n).astype(np.float32)).to(torch.float32)
-        return (sig * 1000).to(torch.long), torch.cat((sig, torch.zeros(1)))
+        return flow_match_schedule(n or self.num_inference_steps)
 
     def _pos(self, T):
         """SinusoidalPositionalEncoding(384) of arange(T) (internvla_n1_arch.py L52-73), fp32 [T, 384]."""
