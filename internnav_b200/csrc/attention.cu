@@ -12,7 +12,8 @@
 // Flash-attention style: a CTA owns 64 query rows of one (sequence, head); 4 warps x 16 rows; K/V streamed in
 // 64-key tiles through a 2-stage cp.async ring; S = QK^T and O += PV on mma.sync.m16n8k16 (bf16, fp32 accumulate)
 // with ldmatrix operand fetch; online softmax in registers with quad shuffles.
-// TODO(round 2): tcgen05 path for the hd-128 prefill (attention is < 5 % of the path's FLOPs).
+// The hd-128 var-len prefill of up to 320 tokens per sequence is routed to the tcgen05 kernel (attention_tc.cu) by
+// attention(); this file keeps the general path (any length, GQA, slotted K/V cache, head_dim 48 / 64 / 80 / 128).
 #include <stdlib.h>
 
 #include "n1_ops.h"
